@@ -1,0 +1,216 @@
+/*
+ * newtonnet_b200 - C ABI of the B200 (sm_100a) energy / force / stress path of NewtonNet.
+ *
+ * The reference (THGLab/NewtonNet v2.1.0) is pure Python/PyTorch and has no FFI of its own; the
+ * entry points below are the "thin custom-op layer" that its hot path
+ *     NewtonNet.forward(z, pos, cell, batch)            newtonnet/models/newtonnet.py:74-104
+ *     MLAseCalculator.calculate                         newtonnet/utils/ase_interface.py:52-81
+ * binds to (ctypes stub in INTEGRATION.md).  Each function cites the reference code it replaces;
+ * citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (inputs, outputs, workspaces); nothing is allocated or freed here,
+ *     except a few KB of lazily created read-only tables;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync inside;
+ *   - return value 0 = launched, negative = error (see nn_last_error(), thread local);
+ *   - device-side conditions (capacity overflow, unsorted batch, singular cell) are reported in a
+ *     caller-provided int32 status word array `status[NN_STATUS_WORDS]`, read back by the caller
+ *     together with the results;
+ *   - fp32 arithmetic, int32 indices; F = 128 features, nb = 20 radial basis functions, SiLU.
+ *   - atoms of one system are contiguous and `batch` is non-decreasing (PyG convention used by the
+ *     reference, newtonnet/utils/ase_interface.py:141).
+ *
+ * Edge convention: directed edge e = (i, j), i = destination = edge_index[0],
+ * j = source = edge_index[1], disp_e = pos_i - pos_j (minimum image).  The neighbour list is a
+ * destination-sorted CSR (row_ptr, col) with rows sorted by j (== the reference's edge order) plus the
+ * list of undirected pairs p = (i < j): message, e1 and e2 are symmetric in (i, j) and are evaluated
+ * once per pair; `edge_pair[e]` = pair id of directed edge e, bit 31 set when the edge is the
+ * reversed orientation (j < i).
+ */
+#ifndef NEWTONNET_B200_H
+#define NEWTONNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NN_API __attribute__((visibility("default")))
+#else
+#define NN_API
+#endif
+
+#define NN_F 128            /* n_features (scripts/config.yml:32) */
+#define NN_NB 20            /* n_basis    (scripts/config.yml:31) */
+#define NN_MAX_LAYERS 8
+#define NN_STATUS_WORDS 8
+/* status word indices */
+#define NN_ST_EDGE_OVERFLOW 0   /* directed edges found > capacity (value = edges needed)            */
+#define NN_ST_ROW_OVERFLOW 1    /* an atom has more than NN_MAX_DEGREE neighbours                    */
+#define NN_ST_BATCH_UNSORTED 2  /* batch is not non-decreasing / out of range                        */
+#define NN_ST_SINGULAR_CELL 3   /* periodic batch with a singular cell (reference: _LinAlgError)     */
+#define NN_ST_N_EDGES 4         /* number of directed edges E                                        */
+#define NN_ST_N_PAIRS 5         /* number of undirected pairs P = E / 2                              */
+#define NN_ST_N_CELLS 6         /* number of grid cells used by the neighbour search                 */
+#define NN_MAX_DEGREE 512
+
+NN_API const char* nn_last_error(void);
+NN_API int nn_version(void);
+/* number of CUDA kernels this library has launched since the last reset (host-side counter). */
+NN_API long long nn_launch_count(int reset);
+/* optional stage profiler: CUDA events recorded on the launching stream around each stage of
+ * nn_nbr_count / nn_nbr_fill / nn_eval; nn_profile_collect (after a stream synchronise) returns summed
+ * milliseconds and sample counts per stage and clears the samples.  Stage ids: 0 neighbour list,
+ * 1 edge geometry, 2 node GEMMs, 3 pair GEMMs, 4 message, 5 aggregate, 6 energy head, 7 reverse pair
+ * gather, 8 reverse message, 9 reverse aggregate, 10 force/virial, 11 other. */
+#define NN_N_STAGES_API 12
+NN_API int nn_profile_enable(int on);
+NN_API int nn_profile_collect(float* ms_per_stage, int* n_per_stage, int n_stages);
+
+/* ------------------------------------------------------------------ weights
+ * Pointers to fp32 device copies of the reference parameters (names: SURVEY.md section 8b).  `W` is the
+ * torch layout [out, in]; `Wt` its transpose [in, out].  Forward products x @ W^T read Wt, backward
+ * products g @ W read W.
+ */
+typedef struct {
+    const float *W1, *W1t, *b1;     /* interaction_layers.l.message_nodepart.0 */
+    const float *W2, *W2t, *b2;     /* interaction_layers.l.message_nodepart.2 */
+    const float *We, *Wet;          /* message_edgepart.weight [F, nb] and its transpose [nb, F] */
+    const float *U1, *U1t, *U2, *U2t; /* equiv_message1.{0,2}.weight */
+    const float *V1, *V1t, *V2, *V2t; /* equiv_message2.{0,2}.weight */
+    const float *Wu, *Wut;          /* equiv_update.weight */
+} nn_layer_weights;
+
+typedef struct {
+    int32_t n_layers;
+    float cutoff;
+    const float* embedding;         /* embedding_layers.node_embedding.weight [119, F] */
+    const float* frequencies;       /* embedding_layers.edge_embedding.embedding.frequencies [nb] */
+    nn_layer_weights layer[NN_MAX_LAYERS];
+    const float *H1, *H1t, *hb1;    /* output_layers.k.layers.0 */
+    const float *H2, *H2t, *hb2;    /* output_layers.k.layers.2 */
+    const float *w3, *hb3;          /* output_layers.k.layers.4  ([1,F], [1]) */
+    const float *scale, *shift;     /* scalers.k.{scale,shift}.weight [119] */
+} nn_weights;
+
+/* ------------------------------------------------------------------ neighbour list
+ * Replaces RadiusGraph.forward, newtonnet/layers/representations.py:57-100 (dense O(N^2) mesh) with a
+ * per-system cell list; each candidate pair is tested with the reference's fp32 arithmetic so the edge
+ * set is bit-identical (diagonal or zero cells; other cells use the same formula with an fp32 inverse).
+ */
+typedef struct {
+    int32_t n_atoms, n_systems;
+    int32_t cap_edges;              /* capacity of col / edge_pair */
+    int32_t cap_pairs;              /* capacity of pair_* (>= cap_edges / 2) */
+    int32_t cap_cells;              /* capacity of the cell arrays (>= 2 * n_atoms + n_systems) */
+    const float* pos;               /* [N,3] */
+    const float* cell;              /* [B,3,3] rows = lattice vectors; all zero = not periodic */
+    const int64_t* batch;           /* [N] system id of each atom, non-decreasing */
+    /* outputs */
+    int32_t* sys_ptr;               /* [B+1] first atom of each system */
+    int32_t* row_ptr;               /* [N+1] */
+    int32_t* col;                   /* [cap_edges] source atom j, ascending within a row */
+    int32_t* edge_pair;             /* [cap_edges] pair id | (reversed << 31) */
+    int32_t* pair_ptr;              /* [N+1] first pair whose lower atom is i */
+    int32_t* pair_i;                /* [cap_pairs] */
+    int32_t* pair_j;                /* [cap_pairs] */
+    float* pair_disp;               /* [cap_pairs,3] pos_i - pos_j, minimum image (reference arithmetic) */
+    int32_t* status;                /* [NN_STATUS_WORDS] */
+    void* workspace;                /* nn_nbr_workspace_bytes() */
+    size_t workspace_bytes;
+} nn_nbr;
+
+NN_API size_t nn_nbr_workspace_bytes(int32_t n_atoms, int32_t n_systems);
+/* pass 1: bins the atoms, counts neighbours, writes sys_ptr, row_ptr and status[NN_ST_N_EDGES]. */
+NN_API int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream);
+/* pass 2: fills col / edge_pair / pair_*; entries beyond the capacities are dropped and flagged. */
+NN_API int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream);
+/* edge_index [2,E] int64 in the reference's order (representations.py:74-82,97). */
+NN_API int nn_nbr_edge_index(const nn_nbr* nl, int64_t* edge_index, int64_t n_edges, void* stream);
+
+/* ------------------------------------------------------------------ dense contraction (F = 128)
+ * Y[M,128] = epilogue( prologue(X)[M,128] @ B[128,128] ), B row-major [K,N].  Replaces the addmm / mm
+ * calls of models/newtonnet.py:209,218,222,230 and models/output.py:98-100 and their autograd
+ * transposes.  `m_dev` (optional) holds the row count on the device; then `m` is the launch capacity.
+ */
+enum { NN_PRO_NONE = 0, NN_PRO_SILU = 1, NN_PRO_ROWSCALE3 = 2 };
+enum { NN_EPI_BIAS = 0, NN_EPI_DSILU = 1, NN_EPI_ADD = 2, NN_EPI_EQUIV_BWD = 3 };
+typedef struct {
+    const float* X; const float* B; float* Y;
+    const float* bias;              /* NN_EPI_BIAS: [128] or NULL */
+    const float* aux1;              /* DSILU: pre-activation [M,128]; ADD: addend [M,128]; EQUIV_BWD: fbar [M,128] */
+    const float* aux2;              /* ROWSCALE3 / EQUIV_BWD: abar [M/3,128] */
+    const float* aux3;              /* EQUIV_BWD: g [M,128] */
+    const int32_t* m_dev; int32_t m_dev_mul;   /* rows = m_dev[0] * m_dev_mul when m_dev != NULL */
+    int32_t m;
+    int32_t prologue, epilogue;
+} nn_gemm_args;
+NN_API int nn_gemm128(const nn_gemm_args* a, void* stream);
+/* backend for nn_gemm128 and nn_eval: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 tensor cores. */
+NN_API int nn_set_gemm_backend(int backend);
+NN_API int nn_get_gemm_backend(void);
+
+/* ------------------------------------------------------------------ whole evaluation
+ * energy[B], forces[N,3], virial[B,3,3] (= -dE/dD, models/output.py:161-165), stress = -virial/det(cell)
+ * (models/output.py:174-180) for NewtonNet.forward with heads energy / gradient_force / stress / virial.
+ * Replaces EmbeddingNet.forward (models/newtonnet.py:139-161), EdgeEmbedding (layers/
+ * representations.py:20-43), InteractionNet.forward x L (models/newtonnet.py:207-237), EnergyOutput +
+ * ScaleShift + EnergyAggregator (models/output.py:98-100,246; layers/scalers.py:55-58) and the
+ * autograd replay of DerivativeProperty._save_grad (models/output.py:66-73) by the hand-derived
+ * reverse sweep of SURVEY.md section 8a row B.
+ */
+typedef struct {
+    const nn_nbr* nbr;
+    const nn_weights* w;
+    const int64_t* z;               /* [N] atomic numbers */
+    int32_t want_forces;            /* 0: energy only (no reverse sweep) */
+    int32_t want_virial;
+    /* outputs */
+    float* energy;                  /* [B] */
+    float* forces;                  /* [N,3] */
+    float* virial;                  /* [B,9] */
+    float* stress;                  /* [B,9] or NULL */
+    float* atom_node;               /* [N,F]   final invariant features (CustomOutputSet.atom_node) */
+    float* force_node;              /* [N,3,F] final equivariant features */
+    void* workspace; size_t workspace_bytes;   /* nn_eval_workspace_bytes() */
+} nn_eval_args;
+NN_API size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, int32_t cap_pairs, int32_t n_layers,
+                               int32_t want_forces);
+NN_API int nn_eval(const nn_eval_args* a, void* stream);
+
+/* ------------------------------------------------------------------ staged operators (also used by
+ * nn_eval; exported for per-kernel parity tests and for the differentiable training path) */
+/* ScaledNorm + PolynomialCutoff * RadialBessel, representations.py:129-131,166-169,233,41:
+ * per pair d, u = disp/d, rbf[nb] = env(d/rc) * sin(f_n d/rc) / (d/rc). */
+NN_API int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
+                     int32_t cap_pairs, float* rbf, float* unit, float* dist, void* stream);
+/* reverse of the above: G_p = dE/d disp_p from rbf_bar [P,nb] and unit_bar [P,3]. */
+NN_API int nn_edge_geom_bwd(const float* rbf_bar, const float* unit_bar, const float* unit, const float* dist,
+                     const float* freq, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
+                     float* disp_bar, void* stream);
+/* m_p = (We rbf_p) * mn_i * mn_j, models/newtonnet.py:210-211. */
+NN_API int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const float* mn, const float* Wet,
+                        float* msg, void* stream);
+/* a_out = a + sum_e m ; f_out = f + sum_e (e1 u + e2 * f_j), models/newtonnet.py:213-227. */
+NN_API int nn_node_aggregate_fwd(const nn_nbr* nl, const float* msg, const float* e1, const float* e2,
+                          const float* unit, const float* a_in, const float* f_in, float* a_out,
+                          float* f_out, int32_t first_layer, void* stream);
+/* a_out = a + sum_c f[c] * g[c], models/newtonnet.py:230-231 (g = f @ Wu^T from nn_gemm128). */
+NN_API int nn_equiv_update_fwd(const float* a_in, const float* f, const float* g, float* a_out, int32_t n_atoms,
+                        void* stream);
+/* atomic energy + scale/shift + per-system sum: models/output.py:100,246, layers/scalers.py:55-58. */
+NN_API int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* b3, const float* scale,
+                       const float* shift, const int64_t* z, const int32_t* sys_ptr, int32_t n_atoms,
+                       int32_t n_systems, float* e_atom, float* energy, void* stream);
+/* F_i = -sum_e sign_e G_p(e); virial with the reference's strain convention. */
+NN_API int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
+                           float* stress, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEWTONNET_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of libnewtonnet_b200.so (declared in include/newtonnet_b200.h).
+
+There is no CPU fallback and no pure-PyTorch fallback: if the CUDA library is missing the import of
+anything that needs it raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libnewtonnet_b200.so')
+
+NN_F = 128
+NN_NB = 20
+NN_MAX_LAYERS = 8
+NN_STATUS_WORDS = 8
+ST_EDGE_OVERFLOW, ST_ROW_OVERFLOW, ST_BATCH_UNSORTED, ST_SINGULAR_CELL, ST_N_EDGES, ST_N_PAIRS, ST_N_CELLS = range(7)
+STAGES = ['nbr', 'geom', 'node_gemm', 'pair_gemm', 'message', 'aggregate', 'head', 'bwd_gather', 'bwd_message',
+          'bwd_aggregate', 'force', 'other']
+PRO_NONE, PRO_SILU, PRO_ROWSCALE3 = 0, 1, 2
+EPI_BIAS, EPI_DSILU, EPI_ADD, EPI_EQUIV_BWD = 0, 1, 2, 3
+
+_fp = C.c_void_p   # device pointers travel as integers
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        'W1', 'W1t', 'b1', 'W2', 'W2t', 'b2', 'We', 'Wet',
+        'U1', 'U1t', 'U2', 'U2t', 'V1', 'V1t', 'V2', 'V2t', 'Wu', 'Wut')]
+
+
+class Weights(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('cutoff', C.c_float), ('embedding', _fp), ('frequencies', _fp),
+                ('layer', LayerWeights * NN_MAX_LAYERS)] + [(n, _fp) for n in (
+                    'H1', 'H1t', 'hb1', 'H2', 'H2t', 'hb2', 'w3', 'hb3', 'scale', 'shift')]
+
+
+class Nbr(C.Structure):
+    _fields_ = [('n_atoms', C.c_int32), ('n_systems', C.c_int32), ('cap_edges', C.c_int32),
+                ('cap_pairs', C.c_int32), ('cap_cells', C.c_int32)] + [(n, _fp) for n in (
+                    'pos', 'cell', 'batch', 'sys_ptr', 'row_ptr', 'col', 'edge_pair', 'pair_ptr', 'pair_i',
+                    'pair_j', 'pair_disp', 'status', 'workspace')] + [('workspace_bytes', C.c_size_t)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('X', _fp), ('B', _fp), ('Y', _fp), ('bias', _fp), ('aux1', _fp), ('aux2', _fp), ('aux3', _fp),
+                ('m_dev', _fp), ('m_dev_mul', C.c_int32), ('m', C.c_int32), ('prologue', C.c_int32),
+                ('epilogue', C.c_int32)]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [('nbr', C.POINTER(Nbr)), ('w', C.POINTER(Weights)), ('z', _fp), ('want_forces', C.c_int32),
+                ('want_virial', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
+                ('atom_node', _fp), ('force_node', _fp), ('workspace', _fp), ('workspace_bytes', C.c_size_t)]
+
+
+# every symbol include/newtonnet_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'nn_last_error': (C.c_char_p, []),
+    'nn_version': (C.c_int, []),
+    'nn_launch_count': (C.c_longlong, [C.c_int]),
+    'nn_profile_enable': (C.c_int, [C.c_int]),
+    'nn_profile_collect': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    'nn_nbr_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'nn_nbr_count': (C.c_int, [C.POINTER(Nbr), C.c_float, _fp]),
+    'nn_nbr_fill': (C.c_int, [C.POINTER(Nbr), C.c_float, _fp]),
+    'nn_nbr_edge_index': (C.c_int, [C.POINTER(Nbr), _fp, C.c_int64, _fp]),
+    'nn_gemm128': (C.c_int, [C.POINTER(GemmArgs), _fp]),
+    'nn_set_gemm_backend': (C.c_int, [C.c_int]),
+    'nn_get_gemm_backend': (C.c_int, []),
+    'nn_eval_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'nn_eval': (C.c_int, [C.POINTER(EvalArgs), _fp]),
+    'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp]),
+    'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
+    'nn_edge_message_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp]),
+    'nn_node_aggregate_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
+    'nn_equiv_update_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int32, _fp]),
+    'nn_energy_head_fwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp]),
+    'nn_force_virial_reduce': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises NativeLibraryError (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` or '
+            f'newtonnet_b200/csrc/build.sh.  newtonnet_b200 has no CPU or PyTorch fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().nn_last_error().decode()
+        raise RuntimeError(f'{what} failed (rc={rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

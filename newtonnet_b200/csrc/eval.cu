@@ -1,0 +1,272 @@
+// nn_eval: one call = one NewtonNet energy (+ forces, virial, stress) evaluation on a prebuilt
+// neighbour list.  Launches the staged kernels on one stream, no host synchronisation, all buffers
+// carved from the caller's workspace; capturable in a CUDA graph.
+//
+// Forward follows NewtonNet.forward (reference newtonnet/models/newtonnet.py:74-104); the reverse
+// sweep is the hand-derived backward of SURVEY.md section 8a row B in pair-symmetric form (checked in
+// fp64 against the reference's autograd by oracle/newtonnet_oracle.py::forward_analytic).
+#include <stdarg.h>
+#include "common.cuh"
+
+int nn_gemm128_simt_launch(const nn_gemm_args& a, cudaStream_t s);
+int nn_gemm128_tc_launch(const nn_gemm_args& a, cudaStream_t s);
+int nn_embed_launch(const int64_t* z, const float* emb, float* a, int N, int* status, cudaStream_t s);
+int nn_energy_head_seed_launch(const float* h2pre, const float* w3, const float* scale, const int64_t* z, int N,
+                               float* gh2, cudaStream_t s);
+int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
+                              float* e2bar, float* ubar, bool first, cudaStream_t s);
+int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* Wet,
+                               float* mbar_io, float* rbf_bar, cudaStream_t s);
+int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
+                                 float* mnbar, float* fbar_new, bool first, cudaStream_t s);
+
+// ---------------------------------------------------------------------------- error / backend state
+static thread_local char g_err[512] = "";
+void nn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* nn_last_error(void) { return g_err; }
+extern "C" int nn_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------- launch counter / stage profiler
+#include <atomic>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+void nn_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long nn_launch_count(int reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+namespace {
+struct ProfSample { cudaEvent_t e0, e1; int stage; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfSample> samples;   // recorded since the last collect
+    std::vector<cudaEvent_t> pool;     // reusable events
+    cudaEvent_t cur0 = nullptr; int cur_stage = -1; int depth = 0;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+} g_prof;
+}  // namespace
+
+void nn_prof_begin(int stage, cudaStream_t s) {
+    if (!g_prof.on) return;
+    if (g_prof.depth++ > 0) return;          // nested scopes belong to the outer stage
+    g_prof.cur0 = g_prof.get(); g_prof.cur_stage = stage;
+    cudaEventRecord(g_prof.cur0, s);
+}
+void nn_prof_end(cudaStream_t s) {
+    if (!g_prof.on) return;
+    if (--g_prof.depth > 0) return;
+    cudaEvent_t e1 = g_prof.get();
+    cudaEventRecord(e1, s);
+    g_prof.samples.push_back({g_prof.cur0, e1, g_prof.cur_stage});
+}
+extern "C" int nn_profile_enable(int on) { g_prof.on = on != 0; g_prof.depth = 0; return 0; }
+// Sums the recorded stage times (ms) and sample counts; the caller must have synchronised the stream.
+extern "C" int nn_profile_collect(float* ms_per_stage, int* n_per_stage, int n_stages) {
+    for (int k = 0; k < n_stages; ++k) { ms_per_stage[k] = 0.f; n_per_stage[k] = 0; }
+    for (auto& sm : g_prof.samples) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sm.e0, sm.e1) == cudaSuccess && sm.stage < n_stages) {
+            ms_per_stage[sm.stage] += ms; n_per_stage[sm.stage] += 1;
+        }
+        g_prof.pool.push_back(sm.e0); g_prof.pool.push_back(sm.e1);
+    }
+    g_prof.samples.clear();
+    return NN_N_STAGES;
+}
+
+static int g_backend = 0;
+extern "C" int nn_set_gemm_backend(int backend) {
+    if (backend != 0 && backend != 1) { nn_set_error("unknown gemm backend %d", backend); return -1; }
+    g_backend = backend;
+    return 0;
+}
+extern "C" int nn_get_gemm_backend(void) { return g_backend; }
+
+int nn_gemm128_launch(const nn_gemm_args& a, cudaStream_t s) {
+    return g_backend == 1 ? nn_gemm128_tc_launch(a, s) : nn_gemm128_simt_launch(a, s);
+}
+extern "C" int nn_gemm128(const nn_gemm_args* a, void* stream) {
+    NN_REQUIRE(a && a->X && a->B && a->Y, "null pointer");
+    return nn_gemm128_launch(*a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- workspace layout
+namespace {
+
+struct LayerBuf {
+    float *pre, *mn, *f_out, *g;          // node level: [N,F], [N,F], [N,3,F], [N,3,F]
+    float *msg, *q1, *e1, *q2, *e2;       // pair level: [P,F] each (q2/e2 unused in layer 0)
+};
+
+struct EvalWs {
+    LayerBuf layer[NN_MAX_LAYERS];
+    float *a0, *a1;                       // [N,F] ping-pong invariant features
+    float *rbf, *unit, *dist;             // [P,nb], [P,3], [P]
+    float *h1pre, *h2pre, *e_atom;        // head
+    // reverse sweep
+    float *abar, *mnbar, *tmpN;           // [N,F]
+    float *fbar, *dfb;                    // [N,3,F]
+    float *e2bar, *mbar;                  // [P,F]
+    float *rbf_bar, *ubar, *G;            // [P,nb], [P,3], [P,3]
+    float *vir_atom;                      // [N,9]
+    size_t total;
+};
+
+EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
+    WsCarver c(base, cap);
+    EvalWs w{};
+    const size_t NF = (size_t)N * kF, PF = (size_t)P * kF;
+    for (int l = 0; l < L; ++l) {
+        LayerBuf& b = w.layer[l];
+        b.pre = c.take<float>(NF); b.mn = c.take<float>(NF);
+        b.f_out = c.take<float>(3 * NF); b.g = c.take<float>(3 * NF);
+        b.msg = c.take<float>(PF); b.q1 = c.take<float>(PF); b.e1 = c.take<float>(PF);
+        if (l > 0) { b.q2 = c.take<float>(PF); b.e2 = c.take<float>(PF); }
+    }
+    w.a0 = c.take<float>(NF); w.a1 = c.take<float>(NF);
+    w.rbf = c.take<float>((size_t)P * kNB); w.unit = c.take<float>((size_t)P * 3); w.dist = c.take<float>(P);
+    w.h1pre = c.take<float>(NF); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
+    if (bwd) {
+        w.abar = c.take<float>(NF); w.mnbar = c.take<float>(NF); w.tmpN = c.take<float>(NF);
+        w.fbar = c.take<float>(3 * NF); w.dfb = c.take<float>(3 * NF);
+        w.e2bar = c.take<float>(PF); w.mbar = c.take<float>(PF);
+        w.rbf_bar = c.take<float>((size_t)P * kNB); w.ubar = c.take<float>((size_t)P * 3); w.G = c.take<float>((size_t)P * 3);
+        w.vir_atom = c.take<float>((size_t)N * 9);
+    }
+    w.total = c.off;
+    return w;
+}
+
+struct Gemm {
+    cudaStream_t s; int rc = 0;
+    void run(const float* X, const float* B, float* Y, int m, int pro, int epi, const float* bias = nullptr,
+             const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
+             const int* m_dev = nullptr, int mul = 1) {
+        if (rc) return;
+        ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
+        nn_gemm_args a{};
+        a.X = X; a.B = B; a.Y = Y; a.bias = bias; a.aux1 = aux1; a.aux2 = aux2; a.aux3 = aux3;
+        a.m_dev = m_dev; a.m_dev_mul = mul; a.m = m; a.prologue = pro; a.epilogue = epi;
+        rc = nn_gemm128_launch(a, s);
+    }
+};
+
+}  // namespace
+
+extern "C" size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, int32_t cap_pairs, int32_t n_layers,
+                                          int32_t want_forces) {
+    (void)n_systems;
+    if (n_layers < 1 || n_layers > NN_MAX_LAYERS) return 0;
+    return carve_eval(nullptr, 0, n_atoms, cap_pairs, n_layers, want_forces != 0).total;
+}
+
+#define NN_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
+    NN_REQUIRE(a && a->nbr && a->w && a->z && a->energy, "null pointer");
+    const nn_nbr* nl = a->nbr;
+    const nn_weights& W = *a->w;
+    const int N = nl->n_atoms, B = nl->n_systems, P = nl->cap_pairs, L = W.n_layers;
+    NN_REQUIRE(L >= 1 && L <= NN_MAX_LAYERS, "n_layers out of range");
+    const bool bwd = a->want_forces != 0 || a->want_virial != 0;
+    NN_REQUIRE(!bwd || a->forces, "forces buffer required");
+    NN_REQUIRE(!a->want_virial || a->virial, "virial buffer required");
+    NN_REQUIRE(a->workspace_bytes >= nn_eval_workspace_bytes(N, B, P, L, bwd), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    EvalWs w = carve_eval(a->workspace, a->workspace_bytes, N, P, L, bwd);
+    const int* np_dev = nl->status + NN_ST_N_PAIRS;
+    Gemm g{s};
+
+    // ---- edge features (R3-R6) and embedding (R1)
+    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.unit, w.dist, s)); }
+    float* a_cur = w.a0;
+    float* a_nxt = w.a1;
+    { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_embed_launch(a->z, W.embedding, a_cur, N, nl->status, s)); }
+
+    // ---- interaction layers (R7)
+    for (int l = 0; l < L; ++l) {
+        const nn_layer_weights& lw = W.layer[l];
+        LayerBuf& b = w.layer[l];
+        const bool first = l == 0;
+        const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
+        g.run(a_cur, lw.W1t, b.pre, N, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
+        g.run(b.pre, lw.W2t, b.mn, N, NN_PRO_SILU, NN_EPI_BIAS, lw.b2);
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_MESSAGE, s); NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s)); }
+        g.run(b.msg, lw.U1t, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.run(b.q1, lw.U2t, b.e1, P, NN_PRO_SILU, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
+            g.run(b.msg, lw.V1t, b.q2, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+            g.run(b.q2, lw.V2t, b.e2, P, NN_PRO_SILU, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        }
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd(nl, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
+        g.run(b.f_out, lw.Wut, b.g, 3 * N, NN_PRO_NONE, NN_EPI_BIAS);
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, N, s)); }
+    }
+
+    // ---- energy head (R8, R9)
+    g.run(a_cur, W.H1t, w.h1pre, N, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
+    g.run(w.h1pre, W.H2t, w.h2pre, N, NN_PRO_SILU, NN_EPI_BIAS, W.hb2);
+    NN_TRY(g.rc);
+    { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd(w.h2pre, W.w3, W.hb3, W.scale, W.shift, a->z, nl->sys_ptr, N, B, w.e_atom, a->energy, s)); }
+    if (a->atom_node) cudaMemcpyAsync(a->atom_node, a_cur, (size_t)N * kF * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (a->force_node) cudaMemcpyAsync(a->force_node, w.layer[L - 1].f_out, (size_t)N * 3 * kF * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, s);
+    if (!bwd) { NN_CHECK_LAUNCH("nn_eval(forward)"); return 0; }
+
+    // ---- reverse sweep (R10 / row B)
+    { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_seed_launch(w.h2pre, W.w3, W.scale, a->z, N, w.tmpN, s)); }   // gh2
+    g.run(w.tmpN, W.H2, w.mnbar, N, NN_PRO_NONE, NN_EPI_DSILU, nullptr, w.h1pre);                    // gh1
+    g.run(w.mnbar, W.H1, w.abar, N, NN_PRO_NONE, NN_EPI_BIAS);                                       // abar
+    NN_TRY(g.rc);
+    cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
+    cudaMemsetAsync(w.rbf_bar, 0, (size_t)P * kNB * sizeof(float), s);
+    cudaMemsetAsync(w.ubar, 0, (size_t)P * 3 * sizeof(float), s);
+    float* fbar = w.fbar;
+    float* dfb = w.dfb;
+    for (int l = L - 1; l >= 0; --l) {
+        const nn_layer_weights& lw = W.layer[l];
+        LayerBuf& b = w.layer[l];
+        const bool first = l == 0;
+        const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
+        // dfb = fbar + abar*g + (abar*f_out) @ Wu
+        g.run(b.f_out, lw.Wu, dfb, 3 * N, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, fbar, w.abar, b.g);
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_BWD_GATHER, s); NN_TRY(nn_pair_bwd_gather_launch(nl, dfb, f_in, w.unit, b.e1, w.e2bar, w.ubar, first, s)); }
+        // mbar = ((e1bar @ U2) * silu'(q1)) @ U1 + ((e2bar @ V2) * silu'(q2)) @ V1
+        g.run(b.e1, lw.U2, b.e1, P, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.q1, nullptr, nullptr, np_dev);
+        g.run(b.e1, lw.U1, w.mbar, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        if (!first) {
+            g.run(w.e2bar, lw.V2, w.e2bar, P, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.q2, nullptr, nullptr, np_dev);
+            g.run(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
+        }
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, lw.Wet, w.mbar, w.rbf_bar, s)); }
+        { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, w.mbar, b.mn, b.e2, dfb, w.mnbar, fbar, first, s)); }
+        // abar += ((mnbar @ W2) * silu'(pre)) @ W1
+        g.run(w.mnbar, lw.W2, w.tmpN, N, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.pre);
+        g.run(w.tmpN, lw.W1, w.abar, N, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
+        NN_TRY(g.rc);
+        // fbar of the next (lower) layer was written into `fbar`; dfb is scratch again
+    }
+    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.rbf_bar, w.ubar, w.unit, w.dist, W.frequencies, W.cutoff, np_dev, P, w.G, s)); }
+    {
+        ProfScope ps(NN_STAGE_FORCE, s);
+        NN_TRY(nn_force_virial_reduce(nl, w.G, a->forces, a->want_virial ? a->virial : nullptr,
+                                      a->want_virial ? a->stress : nullptr, w.vir_atom, s));
+    }
+    NN_CHECK_LAUNCH("nn_eval");
+    return 0;
+}

@@ -1,0 +1,459 @@
+// Neighbour-list build: per-system cell list -> destination-sorted CSR + undirected pair list.
+//
+// Replaces RadiusGraph.forward (reference newtonnet/layers/representations.py:57-100), which builds a
+// dense O(N^2) ordered-pair mesh per system and filters it.  Here candidates come from a grid of cells
+// no smaller than the cutoff; every candidate (i, j) is then tested with the reference's own fp32
+// arithmetic (nn_min_image / nn_norm3 in common.cuh), so the surviving edge set is identical.  All
+// work is HBM/latency-bound integer + fp32 work: warp per atom, coalesced candidate reads, no atomics
+// on the output (two-pass count / fill), rows sorted by source index so the order equals the
+// reference's (i-major, j ascending).
+#include <cub/device/device_scan.cuh>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+struct NbrWs {
+    SysMeta* meta;        // [B]
+    float* bounds;        // [B,6] min xyz, max xyz
+    int* atom_cell;       // [N]
+    int* cell_count;      // [cap_cells+1]
+    int* cell_start;      // [cap_cells+1]
+    int* cell_fill;       // [cap_cells]
+    int* sorted_atoms;    // [N]
+    int* deg;             // [N+1]
+    int* fwd_cnt;         // [N+1]
+    void* scan_tmp; size_t scan_tmp_bytes;
+    size_t total;
+};
+
+size_t scan_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, n);
+    return bytes;
+}
+
+NbrWs carve(void* base, size_t cap, int N, int B) {
+    WsCarver c(base, cap);
+    NbrWs w;
+    int cap_cells = 2 * N + B + 1;
+    w.meta = c.take<SysMeta>(B);
+    w.bounds = c.take<float>((size_t)B * 6);
+    w.atom_cell = c.take<int>(N);
+    w.cell_count = c.take<int>(cap_cells + 1);
+    w.cell_start = c.take<int>(cap_cells + 1);
+    w.cell_fill = c.take<int>(cap_cells);
+    w.sorted_atoms = c.take<int>(N);
+    w.deg = c.take<int>(N + 1);
+    w.fwd_cnt = c.take<int>(N + 1);
+    w.scan_tmp_bytes = scan_temp_bytes(cap_cells + 1 > N + 1 ? cap_cells + 1 : N + 1);
+    w.scan_tmp = c.take<char>(w.scan_tmp_bytes);
+    w.total = c.off;
+    return w;
+}
+
+// ---------------------------------------------------------------- system table
+__global__ void k_sys_ptr(const int64_t* __restrict__ batch, int N, int B, int* __restrict__ sys_ptr,
+                          int* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > N) return;
+    long long prev = (i == 0) ? -1 : batch[i - 1];
+    long long cur = (i == N) ? B : batch[i];
+    if (cur < prev || cur > B || (i < N && cur >= B) || prev < -1) { atomicExch(&status[NN_ST_BATCH_UNSORTED], 1); return; }
+    for (long long s = prev + 1; s <= cur; ++s) sys_ptr[s] = i;
+}
+
+__global__ void k_sys_bounds(const float* __restrict__ pos, const int* __restrict__ sys_ptr,
+                             float* __restrict__ bounds) {
+    int b = blockIdx.x;
+    int first = sys_ptr[b], last = sys_ptr[b + 1];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = first + threadIdx.x; i < last; i += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = pos[3 * i + d];
+            lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v);
+        }
+    }
+    __shared__ float s_lo[3][32], s_hi[3][32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if (lane == 0) { s_lo[d][wid] = lo[d]; s_hi[d][wid] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int d = threadIdx.x;
+        float l = 3.0e38f, h = -3.0e38f;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { l = fminf(l, s_lo[d][w]); h = fmaxf(h, s_hi[d][w]); }
+        bounds[6 * b + d] = l; bounds[6 * b + 3 + d] = h;
+    }
+}
+
+// One block: periodic flag over the whole batch (reference: `not (cell == 0).all()`,
+// representations.py:86 - if ANY entry of ANY cell is non-zero every system takes the solve path),
+// then per-system mode / grid, then an exclusive scan of the grid sizes.
+__global__ void k_sys_plan(const float* __restrict__ cell, const int* __restrict__ sys_ptr,
+                           const float* __restrict__ bounds, int B, float cutoff, SysMeta* __restrict__ meta,
+                           int* __restrict__ status) {
+    __shared__ int s_any;
+    __shared__ int s_carry;
+    __shared__ int s_scan[1024];
+    if (threadIdx.x == 0) { s_any = 0; s_carry = 0; }
+    __syncthreads();
+    int any = 0;
+    for (int k = threadIdx.x; k < B * 9; k += blockDim.x) any |= (cell[k] != 0.0f);
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    const bool periodic = s_any != 0;
+    for (int base = 0; base < B; base += blockDim.x) {
+        int b = base + threadIdx.x;
+        int ncells = 0;
+        SysMeta m;
+        if (b < B) {
+            m.first = sys_ptr[b]; m.count = sys_ptr[b + 1] - sys_ptr[b]; m.pad_ = 0;
+            const float* h = cell + 9 * b;
+            float lo[3] = {bounds[6 * b], bounds[6 * b + 1], bounds[6 * b + 2]};
+            float hi[3] = {bounds[6 * b + 3], bounds[6 * b + 4], bounds[6 * b + 5]};
+            if (m.count == 0) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 0.f; }
+            float amax = 0.f;
+            for (int d = 0; d < 3; ++d) amax = fmaxf(amax, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
+            // smallest admissible grid cell: cutoff + safety for fp32 rounding of pos_i - pos_j
+            double wmin = (double)cutoff * 1.0001 + 16.0 * 1.1920929e-7 * (double)amax;
+            for (int k = 0; k < 9; ++k) { m.H[k] = h[k]; m.Hinv[k] = 0.f; }
+            for (int d = 0; d < 3; ++d) { m.lo[d] = 0.f; m.wsc[d] = 0.f; m.L[d] = 0.f; m.nc[d] = 1; }
+            double ext[3];
+            if (!periodic) {
+                m.mode = 0;
+                for (int d = 0; d < 3; ++d) { ext[d] = fmax((double)hi[d] - (double)lo[d], 1e-6); m.lo[d] = lo[d]; }
+            } else {
+                bool diag = h[1] == 0.f && h[2] == 0.f && h[3] == 0.f && h[5] == 0.f && h[6] == 0.f && h[7] == 0.f;
+                double H[9]; for (int k = 0; k < 9; ++k) H[k] = h[k];
+                double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+                if (det == 0.0) atomicExch(&status[NN_ST_SINGULAR_CELL], 1);
+                if (diag && h[0] > 0.f && h[4] > 0.f && h[8] > 0.f) {
+                    m.mode = 1;
+                    for (int d = 0; d < 3; ++d) { m.L[d] = h[4 * d]; ext[d] = h[4 * d]; }
+                } else {
+                    m.mode = 2;
+                    // inverse of cell^T = (cofactor matrix of cell) / det
+                    double inv = det != 0.0 ? 1.0 / det : 0.0;
+                    double C[9];
+                    C[0] = (H[4] * H[8] - H[5] * H[7]); C[1] = -(H[3] * H[8] - H[5] * H[6]); C[2] = (H[3] * H[7] - H[4] * H[6]);
+                    C[3] = -(H[1] * H[8] - H[2] * H[7]); C[4] = (H[0] * H[8] - H[2] * H[6]); C[5] = -(H[0] * H[7] - H[1] * H[6]);
+                    C[6] = (H[1] * H[5] - H[2] * H[4]); C[7] = -(H[0] * H[5] - H[2] * H[3]); C[8] = (H[0] * H[4] - H[1] * H[3]);
+                    for (int k = 0; k < 9; ++k) m.Hinv[k] = (float)(C[k] * inv);
+                    ext[0] = ext[1] = ext[2] = 0.0;   // single grid cell: all pairs of the system
+                }
+            }
+            long long cap = 2LL * m.count; if (cap < 1) cap = 1;
+            int nc[3];
+            for (int d = 0; d < 3; ++d) {
+                double q = floor(ext[d] / wmin);
+                nc[d] = q < 1.0 ? 1 : (q > 1024.0 ? 1024 : (int)q);
+            }
+            // sparse boxes: coarsen (cells may only get larger) until the grid has <= 2 n_atoms cells
+            while ((long long)nc[0] * nc[1] * nc[2] > cap) {
+                int dmax = 0;
+                if (nc[1] > nc[dmax]) dmax = 1;
+                if (nc[2] > nc[dmax]) dmax = 2;
+                nc[dmax] -= 1;
+            }
+            for (int d = 0; d < 3; ++d) {
+                m.nc[d] = nc[d];
+                m.wsc[d] = (m.mode == 0) ? (float)((double)nc[d] / ext[d]) : (float)nc[d];
+            }
+            ncells = nc[0] * nc[1] * nc[2];
+        }
+        // block exclusive scan of ncells
+        s_scan[threadIdx.x] = ncells;
+        __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {
+            int v = (threadIdx.x >= o) ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (b < B) { m.cell_off = s_carry + s_scan[threadIdx.x] - ncells; meta[b] = m; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry += s_scan[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) status[NN_ST_N_CELLS] = s_carry;
+}
+
+__device__ __forceinline__ void cell_coords(const SysMeta& m, float x, float y, float z, int c[3]) {
+    float p[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int v = 0;
+        if (m.mode == 0) {
+            v = (int)(((double)p[d] - (double)m.lo[d]) * (double)m.wsc[d]);
+        } else if (m.mode == 1) {
+            double f = (double)p[d] / (double)m.L[d];
+            f -= floor(f);
+            v = (int)(f * (double)m.nc[d]);
+        }
+        c[d] = v < 0 ? 0 : (v >= m.nc[d] ? m.nc[d] - 1 : v);
+    }
+}
+
+__global__ void k_bin_count(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
+                            const SysMeta* __restrict__ meta, int* __restrict__ atom_cell,
+                            int* __restrict__ cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const SysMeta& m = meta[batch[i]];
+    int c[3];
+    cell_coords(m, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], c);
+    int cid = m.cell_off + (c[0] * m.nc[1] + c[1]) * m.nc[2] + c[2];
+    atom_cell[i] = cid;
+    atomicAdd(&cell_count[cid], 1);
+}
+
+__global__ void k_bin_fill(int N, const int* __restrict__ atom_cell, const int* __restrict__ cell_start,
+                           int* __restrict__ cell_fill, int* __restrict__ sorted_atoms) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int cid = atom_cell[i];
+    int slot = atomicAdd(&cell_fill[cid], 1);
+    sorted_atoms[cell_start[cid] + slot] = i;   // order inside a cell is irrelevant: rows are sorted later
+}
+
+// Visit every candidate neighbour of atom i once; FILL = false counts, FILL = true collects into smem.
+template <bool FILL>
+__device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __restrict__ pos,
+                                                const SysMeta& m, const int* __restrict__ cell_start,
+                                                const int* __restrict__ sorted_atoms, float cutoff,
+                                                int* __restrict__ row_buf) {
+    const float3 pi = make_float3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    int c[3];
+    cell_coords(m, pi.x, pi.y, pi.z, c);
+    int found = 0;
+    const bool per = m.mode != 0;
+    for (int ox = -1; ox <= 1; ++ox) {
+        int cx = c[0] + ox;
+        if (per) { if ((m.nc[0] == 1 && ox != 0) || (m.nc[0] == 2 && ox < 0)) continue; cx = (cx + m.nc[0]) % m.nc[0]; }
+        else if (cx < 0 || cx >= m.nc[0]) continue;
+        for (int oy = -1; oy <= 1; ++oy) {
+            int cy = c[1] + oy;
+            if (per) { if ((m.nc[1] == 1 && oy != 0) || (m.nc[1] == 2 && oy < 0)) continue; cy = (cy + m.nc[1]) % m.nc[1]; }
+            else if (cy < 0 || cy >= m.nc[1]) continue;
+            for (int oz = -1; oz <= 1; ++oz) {
+                int cz = c[2] + oz;
+                if (per) { if ((m.nc[2] == 1 && oz != 0) || (m.nc[2] == 2 && oz < 0)) continue; cz = (cz + m.nc[2]) % m.nc[2]; }
+                else if (cz < 0 || cz >= m.nc[2]) continue;
+                int cid = m.cell_off + (cx * m.nc[1] + cy) * m.nc[2] + cz;
+                int s0 = cell_start[cid], s1 = cell_start[cid + 1];
+                for (int s = s0 + lane; s - lane < s1; s += 32) {
+                    bool pass = false;
+                    int j = -1;
+                    if (s < s1) {
+                        j = sorted_atoms[s];
+                        if (j != i) {
+                            float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]),
+                                                   __fsub_rn(pi.z, pos[3 * j + 2]));
+                            d = nn_min_image(d, m, nullptr);
+                            pass = nn_norm3(d) < cutoff;
+                        }
+                    }
+                    unsigned mask = __ballot_sync(0xffffffffu, pass);
+                    if (FILL && pass) {
+                        int slot = found + __popc(mask & ((1u << lane) - 1u));
+                        if (slot < NN_MAX_DEGREE) row_buf[slot] = j;
+                    }
+                    found += __popc(mask);
+                }
+            }
+        }
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_nbr_count(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
+            const SysMeta* __restrict__ meta, const int* __restrict__ cell_start,
+            const int* __restrict__ sorted_atoms, float cutoff, int* __restrict__ deg, int* __restrict__ status) {
+    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    SysMeta m = meta[batch[i]];
+    int found = visit_neighbours<false>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, nullptr);
+    if (lane == 0) {
+        if (found > NN_MAX_DEGREE) { atomicMax(&status[NN_ST_ROW_OVERFLOW], found); found = NN_MAX_DEGREE; }
+        deg[i] = found;
+    }
+}
+
+__global__ void k_finish_count(const int* __restrict__ row_ptr, int N, int cap_edges, int* __restrict__ status) {
+    int E = row_ptr[N];
+    status[NN_ST_N_EDGES] = E;
+    status[NN_ST_N_PAIRS] = E / 2;
+    if (E > cap_edges) status[NN_ST_EDGE_OVERFLOW] = E;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_nbr_fill(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
+           const SysMeta* __restrict__ meta, const int* __restrict__ cell_start,
+           const int* __restrict__ sorted_atoms, float cutoff, const int* __restrict__ row_ptr,
+           int cap_edges, int* __restrict__ col, int* __restrict__ fwd_cnt, const int* __restrict__ status) {
+    __shared__ int s_rows[kWarpsPerBlock][NN_MAX_DEGREE];
+    if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x * kWarpsPerBlock + w;
+    if (i >= N) return;
+    SysMeta m = meta[batch[i]];
+    int* buf = s_rows[w];
+    int found = visit_neighbours<true>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, buf);
+    if (found > NN_MAX_DEGREE) found = NN_MAX_DEGREE;
+    __syncwarp();
+    const int base = row_ptr[i];
+    int fwd = 0;
+    // rank sort (rows are short): position of j = number of smaller entries
+    for (int k = lane; k < found; k += 32) {
+        int j = buf[k];
+        int rank = 0;
+        for (int t = 0; t < found; ++t) rank += (buf[t] < j);
+        if (base + rank < cap_edges) col[base + rank] = j;
+        fwd += (j > i);
+    }
+    for (int o = 16; o > 0; o >>= 1) fwd += __shfl_xor_sync(0xffffffffu, fwd, o);
+    if (lane == 0) fwd_cnt[i] = fwd;
+}
+
+// Pair table: forward edges (j > i) are the tail of each sorted row and define the pairs; a reversed
+// edge (j < i) finds its pair by binary search of i in the tail of row j (the edge set is symmetric).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_pair_build(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
+             const SysMeta* __restrict__ meta, const int* __restrict__ row_ptr, const int* __restrict__ col,
+             const int* __restrict__ pair_ptr, int cap_pairs, int* __restrict__ edge_pair,
+             int* __restrict__ pair_i, int* __restrict__ pair_j, float* __restrict__ pair_disp,
+             int* __restrict__ status) {
+    if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
+    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    SysMeta m = meta[batch[i]];
+    const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    const int nfwd = pair_ptr[i + 1] - pair_ptr[i];
+    const int f0 = r1 - nfwd;
+    const float3 pi = make_float3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    for (int e = r0 + lane; e < r1; e += 32) {
+        int j = col[e];
+        if (e >= f0) {
+            int p = pair_ptr[i] + (e - f0);
+            edge_pair[e] = p;
+            if (p < cap_pairs) {
+                pair_i[p] = i; pair_j[p] = j;
+                float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]),
+                                       __fsub_rn(pi.z, pos[3 * j + 2]));
+                d = nn_min_image(d, m, nullptr);
+                pair_disp[3 * p] = d.x; pair_disp[3 * p + 1] = d.y; pair_disp[3 * p + 2] = d.z;
+            } else {
+                atomicMax(&status[NN_ST_EDGE_OVERFLOW], 2 * (p + 1));
+            }
+        } else {
+            int lo = row_ptr[j + 1] - (pair_ptr[j + 1] - pair_ptr[j]), hi = row_ptr[j + 1];
+            const int fj = lo;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (col[mid] < i) lo = mid + 1; else hi = mid; }
+            int p = -1;
+            if (lo < row_ptr[j + 1] && col[lo] == i) p = pair_ptr[j] + (lo - fj);
+            else atomicExch(&status[NN_ST_BATCH_UNSORTED], 2);   // asymmetric edge set: cannot happen
+            edge_pair[e] = p | (int)0x80000000u;
+        }
+    }
+}
+
+__global__ void k_edge_index(const int* __restrict__ row_ptr, const int* __restrict__ col, int N,
+                             long long E, int64_t* __restrict__ edge_index) {
+    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
+        if (e < E) { edge_index[e] = i; edge_index[E + e] = col[e]; }
+    }
+}
+
+}  // namespace
+
+const SysMeta* nn_nbr_sysmeta(const nn_nbr* nl) { return (const SysMeta*)nl->workspace; }
+
+extern "C" size_t nn_nbr_workspace_bytes(int32_t n_atoms, int32_t n_systems) {
+    return carve(nullptr, 0, n_atoms, n_systems).total;
+}
+
+static int check_nbr(const nn_nbr* nl) {
+    NN_REQUIRE(nl != nullptr, "null nn_nbr");
+    NN_REQUIRE(nl->n_atoms >= 0 && nl->n_systems >= 1, "bad sizes");
+    NN_REQUIRE(nl->cap_cells >= 2 * nl->n_atoms + nl->n_systems, "cap_cells < 2*n_atoms + n_systems");
+    NN_REQUIRE(nl->workspace_bytes >= nn_nbr_workspace_bytes(nl->n_atoms, nl->n_systems), "workspace too small");
+    NN_REQUIRE(nl->pos && nl->cell && nl->batch && nl->sys_ptr && nl->row_ptr && nl->status, "null pointer");
+    return 0;
+}
+
+extern "C" int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream) {
+    if (int rc = check_nbr(nl)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(NN_STAGE_NBR, s);
+    const int N = nl->n_atoms, B = nl->n_systems;
+    NbrWs w = carve(nl->workspace, nl->workspace_bytes, N, B);
+    const int cap_cells = 2 * N + B + 1;
+    cudaMemsetAsync(nl->status, 0, NN_STATUS_WORDS * sizeof(int), s);
+    cudaMemsetAsync(w.cell_count, 0, (size_t)(cap_cells + 1) * sizeof(int), s);
+    cudaMemsetAsync(w.cell_fill, 0, (size_t)cap_cells * sizeof(int), s);
+    cudaMemsetAsync(w.deg, 0, (size_t)(N + 1) * sizeof(int), s);
+    cudaMemsetAsync(w.fwd_cnt, 0, (size_t)(N + 1) * sizeof(int), s);
+    k_sys_ptr<<<nn_ceil_div(N + 1, 256), 256, 0, s>>>(nl->batch, N, B, nl->sys_ptr, nl->status); NN_LAUNCHED(1);
+    k_sys_bounds<<<B, 128, 0, s>>>(nl->pos, nl->sys_ptr, w.bounds); NN_LAUNCHED(1);
+    k_sys_plan<<<1, 1024, 0, s>>>(nl->cell, nl->sys_ptr, w.bounds, B, cutoff, w.meta, nl->status); NN_LAUNCHED(1);
+    if (N > 0) {
+        k_bin_count<<<nn_ceil_div(N, 256), 256, 0, s>>>(nl->pos, nl->batch, N, w.meta, w.atom_cell, w.cell_count); NN_LAUNCHED(1);
+        size_t tb = w.scan_tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.cell_count, w.cell_start, cap_cells + 1, s); NN_LAUNCHED(2);
+        k_bin_fill<<<nn_ceil_div(N, 256), 256, 0, s>>>(N, w.atom_cell, w.cell_start, w.cell_fill, w.sorted_atoms); NN_LAUNCHED(1);
+        k_nbr_count<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, w.deg, nl->status); NN_LAUNCHED(1);
+    }
+    size_t tb = w.scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.deg, nl->row_ptr, N + 1, s); NN_LAUNCHED(2);
+    k_finish_count<<<1, 1, 0, s>>>(nl->row_ptr, N, nl->cap_edges, nl->status); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_nbr_count");
+    return 0;
+}
+
+extern "C" int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream) {
+    if (int rc = check_nbr(nl)) return rc;
+    NN_REQUIRE(nl->col && nl->edge_pair && nl->pair_ptr && nl->pair_i && nl->pair_j && nl->pair_disp, "null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(NN_STAGE_NBR, s);
+    const int N = nl->n_atoms, B = nl->n_systems;
+    NbrWs w = carve(nl->workspace, nl->workspace_bytes, N, B);
+    if (N > 0) {
+        k_nbr_fill<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->row_ptr, nl->cap_edges,
+            nl->col, w.fwd_cnt, nl->status); NN_LAUNCHED(1);
+    }
+    size_t tb = w.scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.fwd_cnt, nl->pair_ptr, N + 1, s); NN_LAUNCHED(2);
+    if (N > 0) {
+        k_pair_build<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            nl->pos, nl->batch, N, w.meta, nl->row_ptr, nl->col, nl->pair_ptr, nl->cap_pairs, nl->edge_pair,
+            nl->pair_i, nl->pair_j, nl->pair_disp, nl->status); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("nn_nbr_fill");
+    return 0;
+}
+
+extern "C" int nn_nbr_edge_index(const nn_nbr* nl, int64_t* edge_index, int64_t n_edges, void* stream) {
+    NN_REQUIRE(nl && edge_index, "null pointer");
+    if (nl->n_atoms == 0 || n_edges == 0) return 0;
+    k_edge_index<<<nn_ceil_div(nl->n_atoms, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        nl->row_ptr, nl->col, nl->n_atoms, n_edges, edge_index); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_nbr_edge_index");
+    return 0;
+}

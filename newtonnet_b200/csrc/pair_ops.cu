@@ -1,0 +1,596 @@
+// Edge-stream kernels of the interaction layers: pair geometry, message, destination-sorted gather /
+// reduce (forward and reverse sweep), energy head, force / virial reduction.
+//
+// All of these are HBM / L2-bandwidth-bound row streams: one warp owns one 128-float feature row
+// (float4 per lane, 512 B fully coalesced), the per-atom sums run over the destination-sorted CSR in a
+// fixed order (deterministic, no atomics - the reference's scatter_add_ is atomic on CUDA).
+//
+// Reference code replaced (paths relative to the reference repo):
+//   ScaledNorm / PolynomialCutoff / RadialBesselLayer   newtonnet/layers/representations.py:118-133,155-171,223-235
+//   InteractionNet.forward (message, scatter, update)   newtonnet/models/newtonnet.py:207-237
+//   EnergyOutput last layer, ScaleShift, EnergyAggregator  newtonnet/models/output.py:98-100,246; layers/scalers.py:55-58
+//   DerivativeProperty._save_grad (autograd replay)     newtonnet/models/output.py:66-73  -> SURVEY.md section 8a row B
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ int dev_count(const int* n_dev, int cap) {
+    int n = n_dev ? *n_dev : cap;
+    return n < cap ? n : cap;
+}
+
+// ---------------------------------------------------------------------------- geometry
+// env(x) = 1 - 55x^9 + 99x^10 - 45x^11 = (1-x)^3 * sum_{k=0..8} C(k+2,2) x^k  (exact identity, see
+// tests/test_oracle.py::test_cutoff_envelope_factorisation); the factored form has no cancellation
+// near the cutoff.  env'(x) = -495 x^8 (1-x)^2.
+__device__ __forceinline__ float envelope(float x) {
+    float p = 45.f;
+    p = fmaf(p, x, 36.f); p = fmaf(p, x, 28.f); p = fmaf(p, x, 21.f); p = fmaf(p, x, 15.f);
+    p = fmaf(p, x, 10.f); p = fmaf(p, x, 6.f); p = fmaf(p, x, 3.f); p = fmaf(p, x, 1.f);
+    float t = 1.0f - x;
+    return t * t * t * p;
+}
+__device__ __forceinline__ float envelope_grad(float x) {
+    float x2 = x * x, x4 = x2 * x2, t = 1.0f - x;
+    return -495.f * x4 * x4 * t * t;
+}
+
+__global__ void k_edge_geom_fwd(const float* __restrict__ disp, const float* __restrict__ freq, float cutoff,
+                                const int* __restrict__ n_dev, int cap, float* __restrict__ rbf,
+                                float* __restrict__ unit, float* __restrict__ dist) {
+    const int P = dev_count(n_dev, cap);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        float3 d3 = make_float3(disp[3 * p], disp[3 * p + 1], disp[3 * p + 2]);
+        float d = nn_norm3(d3);
+        unit[3 * p] = __fdiv_rn(d3.x, d); unit[3 * p + 1] = __fdiv_rn(d3.y, d); unit[3 * p + 2] = __fdiv_rn(d3.z, d);
+        dist[p] = d;
+        float x = __fdiv_rn(d, cutoff);
+        float s = envelope(x) / x;
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) rbf[(size_t)p * kNB + n] = s * sinf(freq[n] * x);
+    }
+}
+
+// G_p = dE/d disp_p = (xbar / rc) u + (ubar - <ubar,u> u) / d,
+// xbar = sum_n rbfbar_n (env' sb_n + env sb'_n), sb_n = sin(f x)/x, sb'_n = (f x cos(f x) - sin(f x))/x^2.
+__global__ void k_edge_geom_bwd(const float* __restrict__ rbf_bar, const float* __restrict__ unit_bar,
+                                const float* __restrict__ unit, const float* __restrict__ dist,
+                                const float* __restrict__ freq, float cutoff, const int* __restrict__ n_dev,
+                                int cap, float* __restrict__ disp_bar) {
+    const int P = dev_count(n_dev, cap);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        float d = dist[p];
+        float x = __fdiv_rn(d, cutoff);
+        float env = envelope(x), envp = envelope_grad(x);
+        float invx = 1.0f / x;
+        float xbar = 0.f;
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) {
+            float fx = freq[n] * x, sn, cs;
+            sincosf(fx, &sn, &cs);
+            float sb = sn * invx;
+            float sbp = (fx * cs - sn) * invx * invx;
+            xbar = fmaf(rbf_bar[(size_t)p * kNB + n], fmaf(envp, sb, env * sbp), xbar);
+        }
+        float3 u = make_float3(unit[3 * p], unit[3 * p + 1], unit[3 * p + 2]);
+        float3 ub = make_float3(unit_bar[3 * p], unit_bar[3 * p + 1], unit_bar[3 * p + 2]);
+        float dot = ub.x * u.x + ub.y * u.y + ub.z * u.z;
+        float a = xbar / cutoff, invd = 1.0f / d;
+        disp_bar[3 * p] = fmaf(a, u.x, (ub.x - dot * u.x) * invd);
+        disp_bar[3 * p + 1] = fmaf(a, u.y, (ub.y - dot * u.y) * invd);
+        disp_bar[3 * p + 2] = fmaf(a, u.z, (ub.z - dot * u.z) * invd);
+    }
+}
+
+// ---------------------------------------------------------------------------- message (forward)
+// me = We rbf_p (K = 20, SIMT: 0.4 % of the layer's FLOPs), m_p = me * (mn_i * mn_j).
+__device__ __forceinline__ float4 edge_part(const float* __restrict__ s_wet, const float* __restrict__ rbf_row,
+                                            int lane) {
+    float4 me = f4_zero();
+#pragma unroll 1
+    for (int q = 0; q < kNB / 4; ++q) {
+        float4 r = ld4(rbf_row + 4 * q);          // same address in all lanes: one broadcast transaction
+        me = f4_fma(r.x, ld4(s_wet + (4 * q + 0) * kF + 4 * lane), me);
+        me = f4_fma(r.y, ld4(s_wet + (4 * q + 1) * kF + 4 * lane), me);
+        me = f4_fma(r.z, ld4(s_wet + (4 * q + 2) * kF + 4 * lane), me);
+        me = f4_fma(r.w, ld4(s_wet + (4 * q + 3) * kF + 4 * lane), me);
+    }
+    return me;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_edge_message_fwd(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
+                   int cap, const float* __restrict__ rbf, const float* __restrict__ mn,
+                   const float* __restrict__ Wet, float* __restrict__ msg) {
+    __shared__ __align__(16) float s_wet[kNB * kF];
+    for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
+    __syncthreads();
+    const int P = dev_count(n_dev, cap);
+    const int lane = threadIdx.x & 31;
+    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
+        int i = pair_i[p], j = pair_j[p];
+        float4 a = ld4(mn + (size_t)i * kF + 4 * lane);
+        float4 b = ld4(mn + (size_t)j * kF + 4 * lane);
+        float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
+        st4(msg + (size_t)p * kF + 4 * lane, f4_mul(me, f4_mul(a, b)));
+    }
+}
+
+// ---------------------------------------------------------------------------- gather / reduce (forward)
+// a_out_i = a_i + sum_{e->i} m_p(e);  f_out_i[c] = f_i[c] + sum_{e->i} (s_e u_p[c] e1_p + e2_p * f_j[c])
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+k_node_aggregate_fwd(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
+                     int N, const float* __restrict__ msg, const float* __restrict__ e1,
+                     const float* __restrict__ e2, const float* __restrict__ unit, const float* __restrict__ a_in,
+                     const float* __restrict__ f_in, float* __restrict__ a_out, float* __restrict__ f_out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= N) return;
+    const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
+    for (int e0 = r0; e0 < r1; e0 += 32) {
+        int my_p = 0, my_j = 0;
+        float ux = 0.f, uy = 0.f, uz = 0.f;
+        if (e0 + lane < r1) {
+            int ep = edge_pair[e0 + lane];
+            my_j = col[e0 + lane];
+            my_p = ep & 0x7fffffff;
+            float sgn = ep < 0 ? -1.0f : 1.0f;
+            ux = sgn * unit[3 * my_p]; uy = sgn * unit[3 * my_p + 1]; uz = sgn * unit[3 * my_p + 2];
+        }
+        const int cnt = min(32, r1 - e0);
+        for (int t = 0; t < cnt; ++t) {
+            const int p = __shfl_sync(0xffffffffu, my_p, t);
+            const float sx = __shfl_sync(0xffffffffu, ux, t), sy = __shfl_sync(0xffffffffu, uy, t),
+                        sz = __shfl_sync(0xffffffffu, uz, t);
+            const size_t po = (size_t)p * kF + 4 * lane;
+            am = f4_add(am, ld4(msg + po));
+            float4 v1 = ld4(e1 + po);
+            fx = f4_fma(sx, v1, fx); fy = f4_fma(sy, v1, fy); fz = f4_fma(sz, v1, fz);
+            if (!FIRST) {
+                const int j = __shfl_sync(0xffffffffu, my_j, t);
+                float4 v2 = ld4(e2 + po);
+                const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
+                fx = f4_fma(v2, ld4(fj), fx); fy = f4_fma(v2, ld4(fj + kF), fy); fz = f4_fma(v2, ld4(fj + 2 * kF), fz);
+            }
+        }
+    }
+    st4(a_out + (size_t)i * kF + 4 * lane, f4_add(ld4(a_in + (size_t)i * kF + 4 * lane), am));
+    float* fo = f_out + (size_t)i * 3 * kF + 4 * lane;
+    if (FIRST) {
+        st4(fo, fx); st4(fo + kF, fy); st4(fo + 2 * kF, fz);
+    } else {
+        const float* fi = f_in + (size_t)i * 3 * kF + 4 * lane;
+        st4(fo, f4_add(ld4(fi), fx)); st4(fo + kF, f4_add(ld4(fi + kF), fy)); st4(fo + 2 * kF, f4_add(ld4(fi + 2 * kF), fz));
+    }
+}
+
+__global__ void k_equiv_update_fwd(const float* __restrict__ a_in, const float* __restrict__ f,
+                                   const float* __restrict__ g, float* __restrict__ a_out, int N) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;       // one float4 of one atom
+    if (t >= N * (kF / 4)) return;
+    int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
+    const float* fi = f + (size_t)i * 3 * kF + q;
+    const float* gi = g + (size_t)i * 3 * kF + q;
+    float4 acc = ld4(a_in + (size_t)i * kF + q);
+    acc = f4_fma(ld4(fi), ld4(gi), acc);
+    acc = f4_fma(ld4(fi + kF), ld4(gi + kF), acc);
+    acc = f4_fma(ld4(fi + 2 * kF), ld4(gi + 2 * kF), acc);
+    st4(a_out + (size_t)i * kF + q, acc);
+}
+
+__global__ void k_embed(const int64_t* __restrict__ z, const float* __restrict__ emb, float* __restrict__ a, int N,
+                        int* __restrict__ status) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * (kF / 4)) return;
+    int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
+    long long zi = z[i];
+    if (zi < 0 || zi > 118) { zi = 0; atomicExch(&status[NN_ST_BATCH_UNSORTED], 3); }
+    st4(a + (size_t)i * kF + q, ld4(emb + (size_t)zi * kF + q));
+}
+
+// ---------------------------------------------------------------------------- energy head
+__global__ void __launch_bounds__(kThreads)
+k_energy_atom(const float* __restrict__ h2pre, const float* __restrict__ w3, const float* __restrict__ b3,
+              const float* __restrict__ scale, const float* __restrict__ shift, const int64_t* __restrict__ z,
+              int N, float* __restrict__ e_atom) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= N) return;
+    float4 h = ld4(h2pre + (size_t)i * kF + 4 * lane);
+    h.x = silu_f(h.x); h.y = silu_f(h.y); h.z = silu_f(h.z); h.w = silu_f(h.w);
+    float o = warp_sum(f4_dot(h, ld4(w3 + 4 * lane)));
+    if (lane == 0) {
+        long long zi = z[i]; if (zi < 0 || zi > 118) zi = 0;
+        e_atom[i] = fmaf(o + b3[0], scale[zi], shift[zi]);
+    }
+}
+
+// fixed-order fp64 sum per system (the reference sums sequentially in fp32; |shift| makes E large)
+__global__ void k_energy_sum(const float* __restrict__ e_atom, const int* __restrict__ sys_ptr,
+                             float* __restrict__ energy) {
+    __shared__ double s[kThreads];
+    int b = blockIdx.x;
+    double acc = 0.0;
+    for (int i = sys_ptr[b] + threadIdx.x; i < sys_ptr[b + 1]; i += kThreads) acc += (double)e_atom[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) energy[b] = (float)s[0];
+}
+
+// dE/d h2pre = scale[z] * w3 * silu'(h2pre)
+__global__ void k_energy_head_seed(const float* __restrict__ h2pre, const float* __restrict__ w3,
+                                   const float* __restrict__ scale, const int64_t* __restrict__ z, int N,
+                                   float* __restrict__ gh2) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * (kF / 4)) return;
+    int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
+    long long zi = z[i]; if (zi < 0 || zi > 118) zi = 0;
+    float sc = scale[zi];
+    float4 h = ld4(h2pre + (size_t)i * kF + q), w = ld4(w3 + q);
+    st4(gh2 + (size_t)i * kF + q, make_float4(sc * w.x * dsilu_f(h.x), sc * w.y * dsilu_f(h.y),
+                                             sc * w.z * dsilu_f(h.z), sc * w.w * dsilu_f(h.w)));
+}
+
+// ---------------------------------------------------------------------------- reverse sweep, pair side
+// w[c] = dfb_i[c] - dfb_j[c];  e1bar = sum_c w[c] u[c] (overwrites e1);  ubar[c] += <w[c], e1>;
+// e2bar = sum_c dfb_i[c] * f_in_j[c] + dfb_j[c] * f_in_i[c]
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+k_pair_bwd_gather(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
+                  int cap, const float* __restrict__ dfb, const float* __restrict__ f_in,
+                  const float* __restrict__ unit, float* __restrict__ e1_io, float* __restrict__ e2bar,
+                  float* __restrict__ ubar) {
+    const int P = dev_count(n_dev, cap);
+    const int lane = threadIdx.x & 31;
+    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
+        const int i = pair_i[p], j = pair_j[p];
+        const float* di = dfb + (size_t)i * 3 * kF + 4 * lane;
+        const float* dj = dfb + (size_t)j * 3 * kF + 4 * lane;
+        float4 dix = ld4(di), diy = ld4(di + kF), diz = ld4(di + 2 * kF);
+        float4 djx = ld4(dj), djy = ld4(dj + kF), djz = ld4(dj + 2 * kF);
+        float4 wx = f4_sub(dix, djx), wy = f4_sub(diy, djy), wz = f4_sub(diz, djz);
+        const float ux = unit[3 * p], uy = unit[3 * p + 1], uz = unit[3 * p + 2];
+        const size_t po = (size_t)p * kF + 4 * lane;
+        float4 v1 = ld4(e1_io + po);
+        float sx = warp_sum(f4_dot(wx, v1)), sy = warp_sum(f4_dot(wy, v1)), sz = warp_sum(f4_dot(wz, v1));
+        if (lane == 0) { ubar[3 * p] += sx; ubar[3 * p + 1] += sy; ubar[3 * p + 2] += sz; }
+        float4 e1b = make_float4(0.f, 0.f, 0.f, 0.f);
+        e1b = f4_fma(ux, wx, e1b); e1b = f4_fma(uy, wy, e1b); e1b = f4_fma(uz, wz, e1b);
+        st4(e1_io + po, e1b);
+        if (!FIRST) {
+            const float* fi = f_in + (size_t)i * 3 * kF + 4 * lane;
+            const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
+            float4 acc = f4_mul(dix, ld4(fj));
+            acc = f4_fma(diy, ld4(fj + kF), acc); acc = f4_fma(diz, ld4(fj + 2 * kF), acc);
+            acc = f4_fma(djx, ld4(fi), acc); acc = f4_fma(djy, ld4(fi + kF), acc); acc = f4_fma(djz, ld4(fi + 2 * kF), acc);
+            st4(e2bar + po, acc);
+        }
+    }
+}
+
+// mtot = mbar + abar_i + abar_j;  rbfbar += (mtot * mn_i * mn_j) We;  t = mtot * me  (overwrites mbar)
+__global__ void __launch_bounds__(kThreads, 3)
+k_pair_bwd_message(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
+                   int cap, const float* __restrict__ abar, const float* __restrict__ mn,
+                   const float* __restrict__ rbf, const float* __restrict__ Wet, float* __restrict__ mbar_io,
+                   float* __restrict__ rbf_bar) {
+    __shared__ __align__(16) float s_wet[kNB * kF];
+    for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
+    __syncthreads();
+    const int P = dev_count(n_dev, cap);
+    const int lane = threadIdx.x & 31;
+    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
+        const int i = pair_i[p], j = pair_j[p];
+        const size_t po = (size_t)p * kF + 4 * lane;
+        float4 mt = ld4(mbar_io + po);
+        mt = f4_add(mt, f4_add(ld4(abar + (size_t)i * kF + 4 * lane), ld4(abar + (size_t)j * kF + 4 * lane)));
+        float4 prod = f4_mul(ld4(mn + (size_t)i * kF + 4 * lane), ld4(mn + (size_t)j * kF + 4 * lane));
+        float4 y = f4_mul(mt, prod);
+        // rbfbar_n = sum_f y_f We[f,n]: per-lane partials, then a warp reduction per basis function
+        float mine = 0.f;
+#pragma unroll 4
+        for (int n = 0; n < kNB; ++n) {
+            float part = warp_sum(f4_dot(y, ld4(s_wet + n * kF + 4 * lane)));
+            if (lane == n) mine = part;
+        }
+        if (lane < kNB) rbf_bar[(size_t)p * kNB + lane] += mine;
+        float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
+        st4(mbar_io + po, f4_mul(mt, me));
+    }
+}
+
+// mnbar_k = sum_{e=(k,i)} t_p * mn_i ;  fbar_new_k[c] = dfb_k[c] + sum_{e=(k,i)} dfb_i[c] * e2_p
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+k_node_aggregate_bwd(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
+                     int N, const float* __restrict__ t, const float* __restrict__ mn, const float* __restrict__ e2,
+                     const float* __restrict__ dfb, float* __restrict__ mnbar, float* __restrict__ fbar_new) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (k >= N) return;
+    const int r0 = row_ptr[k], r1 = row_ptr[k + 1];
+    float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
+    for (int e0 = r0; e0 < r1; e0 += 32) {
+        int my_p = 0, my_i = 0;
+        if (e0 + lane < r1) { my_p = edge_pair[e0 + lane] & 0x7fffffff; my_i = col[e0 + lane]; }
+        const int cnt = min(32, r1 - e0);
+        for (int s = 0; s < cnt; ++s) {
+            const int p = __shfl_sync(0xffffffffu, my_p, s);
+            const int i = __shfl_sync(0xffffffffu, my_i, s);
+            const size_t po = (size_t)p * kF + 4 * lane;
+            am = f4_fma(ld4(t + po), ld4(mn + (size_t)i * kF + 4 * lane), am);
+            if (!FIRST) {
+                float4 v2 = ld4(e2 + po);
+                const float* di = dfb + (size_t)i * 3 * kF + 4 * lane;
+                fx = f4_fma(v2, ld4(di), fx); fy = f4_fma(v2, ld4(di + kF), fy); fz = f4_fma(v2, ld4(di + 2 * kF), fz);
+            }
+        }
+    }
+    st4(mnbar + (size_t)k * kF + 4 * lane, am);
+    if (!FIRST) {
+        const float* dk = dfb + (size_t)k * 3 * kF + 4 * lane;
+        float* fo = fbar_new + (size_t)k * 3 * kF + 4 * lane;
+        st4(fo, f4_add(ld4(dk), fx)); st4(fo + kF, f4_add(ld4(dk + kF), fy)); st4(fo + 2 * kF, f4_add(ld4(dk + 2 * kF), fz));
+    }
+}
+
+// ---------------------------------------------------------------------------- forces and virial
+// F_i = -sum_{e=(i,j)} s_e G_p(e).  Virial with the reference's strain convention
+// (models/newtonnet.py:153-155: pos' = pos @ S, cell' = cell @ S, shift = cell' @ n):
+//   M[a,b] = sum_p dpos_a G_b - (cell^T G)_a n_b,  dE/dD = (M + M^T)/2, virial = -dE/dD.
+// With dpos = disp + cell n:  sym(M) = sym(disp (x) G) + sym(X),  X[a,b] = (cell n)_a G_b - (cell^T G)_a n_b.
+// sym(X) vanishes for cubic cells, is (L_a - L_b)(n_a G_b - G_a n_b)/2 for diagonal cells, and is the
+// reference's (unphysical but reproducible) extra term otherwise.  Each atom accumulates its forward
+// pairs; systems are summed in fp64 in fixed order.
+__global__ void __launch_bounds__(128)
+k_force_virial_atom(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
+                    int N, const float* __restrict__ G, const float* __restrict__ pair_disp,
+                    const float* __restrict__ pos, const int64_t* __restrict__ batch,
+                    const SysMeta* __restrict__ meta, float* __restrict__ forces, float* __restrict__ vir_atom) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool want_vir = vir_atom != nullptr;
+    SysMeta sm;
+    sm.mode = 0;
+    float3 pi = make_float3(0.f, 0.f, 0.f);
+    bool quirk = false;
+    if (want_vir) {
+        sm = meta[batch[i]];
+        pi = make_float3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        quirk = sm.mode == 2 || (sm.mode == 1 && !(sm.L[0] == sm.L[1] && sm.L[1] == sm.L[2]));
+    }
+    for (int e = r0; e < r1; ++e) {
+        int ep = edge_pair[e];
+        int p = ep & 0x7fffffff;
+        float gg[3] = {G[3 * p], G[3 * p + 1], G[3 * p + 2]};
+        if (ep < 0) { fx += gg[0]; fy += gg[1]; fz += gg[2]; continue; }
+        fx -= gg[0]; fy -= gg[1]; fz -= gg[2];
+        if (!want_vir) continue;
+        float dp[3] = {pair_disp[3 * p], pair_disp[3 * p + 1], pair_disp[3 * p + 2]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.5f * (dp[a] * gg[b] + dp[b] * gg[a]);
+        if (quirk) {
+            int j = col[e];
+            float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]), __fsub_rn(pi.z, pos[3 * j + 2]));
+            float3 n3;
+            nn_min_image(d, sm, &n3);
+            float nn[3] = {n3.x, n3.y, n3.z};
+            float X[9];
+            if (sm.mode == 1) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) X[3 * a + b] = sm.L[a] * (nn[a] * gg[b] - gg[a] * nn[b]);
+            } else {
+                float hn[3], hg[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    hn[a] = sm.H[3 * a] * nn[0] + sm.H[3 * a + 1] * nn[1] + sm.H[3 * a + 2] * nn[2];
+                    hg[a] = sm.H[a] * gg[0] + sm.H[3 + a] * gg[1] + sm.H[6 + a] * gg[2];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) X[3 * a + b] = hn[a] * gg[b] - hg[a] * nn[b];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.5f * (X[3 * a + b] + X[3 * b + a]);
+        }
+    }
+    forces[3 * i] = fx; forces[3 * i + 1] = fy; forces[3 * i + 2] = fz;
+    if (want_vir) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vir_atom[(size_t)i * 9 + k] = m[k];
+    }
+}
+
+__global__ void k_virial_sum(const float* __restrict__ vir_atom, const int* __restrict__ sys_ptr,
+                             const float* __restrict__ cell, float* __restrict__ virial, float* __restrict__ stress) {
+    __shared__ double s[kThreads][9];
+    int b = blockIdx.x;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = sys_ptr[b] + threadIdx.x; i < sys_ptr[b + 1]; i += kThreads)
+        for (int k = 0; k < 9; ++k) acc[k] += (double)vir_atom[(size_t)i * 9 + k];
+    for (int k = 0; k < 9; ++k) s[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int k = 0; k < 9; ++k) s[threadIdx.x][k] += s[threadIdx.x + o][k];
+        __syncthreads();
+    }
+    if (threadIdx.x < 9) {
+        int a = threadIdx.x / 3, c = threadIdx.x % 3;
+        double gd = 0.5 * (s[0][3 * a + c] + s[0][3 * c + a]);      // dE/dD
+        virial[9 * b + threadIdx.x] = (float)(-gd);
+        if (stress) {
+            const float* h = cell + 9 * b;
+            // fp32 determinant like torch.det on the fp32 cell (models/output.py:177)
+            double det = (double)h[0] * ((double)h[4] * h[8] - (double)h[5] * h[7]) -
+                         (double)h[1] * ((double)h[3] * h[8] - (double)h[5] * h[6]) +
+                         (double)h[2] * ((double)h[3] * h[7] - (double)h[4] * h[6]);
+            stress[9 * b + threadIdx.x] = (float)(gd / det);
+        }
+    }
+}
+
+int grid_for_rows(long long rows) {
+    long long g = (rows + kWarps - 1) / kWarps;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// ============================================================================ host launchers
+extern "C" int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
+                                int32_t cap_pairs, float* rbf, float* unit, float* dist, void* stream) {
+    if (cap_pairs <= 0) return 0;
+    int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
+    k_edge_geom_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, unit, dist); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_edge_geom_fwd");
+    return 0;
+}
+
+extern "C" int nn_edge_geom_bwd(const float* rbf_bar, const float* unit_bar, const float* unit, const float* dist,
+                                const float* freq, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
+                                float* disp_bar, void* stream) {
+    if (cap_pairs <= 0) return 0;
+    int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
+    k_edge_geom_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(rbf_bar, unit_bar, unit, dist, freq, cutoff, n_pairs_dev,
+                                                           cap_pairs, disp_bar); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_edge_geom_bwd");
+    return 0;
+}
+
+extern "C" int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const float* mn, const float* Wet, float* msg,
+                                   void* stream) {
+    if (nl->cap_pairs <= 0) return 0;
+    k_edge_message_fwd<<<grid_for_rows(nl->cap_pairs), kThreads, 0, (cudaStream_t)stream>>>(
+        nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs, rbf, mn, Wet, msg); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_edge_message_fwd");
+    return 0;
+}
+
+extern "C" int nn_node_aggregate_fwd(const nn_nbr* nl, const float* msg, const float* e1, const float* e2,
+                                     const float* unit, const float* a_in, const float* f_in, float* a_out,
+                                     float* f_out, int32_t first_layer, void* stream) {
+    const int N = nl->n_atoms;
+    if (N <= 0) return 0;
+    int grid = nn_ceil_div(N, kWarps);
+    if (first_layer) {
+        k_node_aggregate_fwd<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+                                                                                e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
+    }
+    else {
+        k_node_aggregate_fwd<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+                                                                                 e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("nn_node_aggregate_fwd");
+    return 0;
+}
+
+extern "C" int nn_equiv_update_fwd(const float* a_in, const float* f, const float* g, float* a_out, int32_t n_atoms,
+                                   void* stream) {
+    if (n_atoms <= 0) return 0;
+    k_equiv_update_fwd<<<nn_ceil_div((long long)n_atoms * (kF / 4), 256), 256, 0, (cudaStream_t)stream>>>(a_in, f, g, a_out, n_atoms); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_equiv_update_fwd");
+    return 0;
+}
+
+extern "C" int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* b3, const float* scale,
+                                  const float* shift, const int64_t* z, const int32_t* sys_ptr, int32_t n_atoms,
+                                  int32_t n_systems, float* e_atom, float* energy, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_atoms > 0) {
+        k_energy_atom<<<nn_ceil_div(n_atoms, kWarps), kThreads, 0, s>>>(h2pre, w3, b3, scale, shift, z, n_atoms, e_atom); NN_LAUNCHED(1);
+    }
+    k_energy_sum<<<n_systems, kThreads, 0, s>>>(e_atom, sys_ptr, energy); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_energy_head_fwd");
+    return 0;
+}
+
+extern "C" int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
+                                      float* stress, void* workspace, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = nl->n_atoms;
+    float* vir_atom = virial ? (float*)workspace : nullptr;
+    NN_REQUIRE(!virial || workspace, "virial needs a workspace of n_atoms*9 floats");
+    if (N > 0) {
+        k_force_virial_atom<<<nn_ceil_div(N, 128), 128, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, disp_bar,
+                                                                 nl->pair_disp, nl->pos, nl->batch, nn_nbr_sysmeta(nl),
+                                                                 forces, vir_atom); NN_LAUNCHED(1);
+    }
+    if (virial) {
+        k_virial_sum<<<nl->n_systems, kThreads, 0, s>>>(vir_atom, nl->sys_ptr, nl->cell, virial, stress); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("nn_force_virial_reduce");
+    return 0;
+}
+
+// ---- launchers used only by nn_eval (eval.cu)
+int nn_embed_launch(const int64_t* z, const float* emb, float* a, int N, int* status, cudaStream_t s) {
+    if (N <= 0) return 0;
+    k_embed<<<nn_ceil_div((long long)N * (kF / 4), 256), 256, 0, s>>>(z, emb, a, N, status); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("embed");
+    return 0;
+}
+int nn_energy_head_seed_launch(const float* h2pre, const float* w3, const float* scale, const int64_t* z, int N,
+                               float* gh2, cudaStream_t s) {
+    if (N <= 0) return 0;
+    k_energy_head_seed<<<nn_ceil_div((long long)N * (kF / 4), 256), 256, 0, s>>>(h2pre, w3, scale, z, N, gh2); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("energy_head_seed");
+    return 0;
+}
+int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
+                              float* e2bar, float* ubar, bool first, cudaStream_t s) {
+    if (nl->cap_pairs <= 0) return 0;
+    int grid = grid_for_rows(nl->cap_pairs);
+    if (first) {
+        k_pair_bwd_gather<true><<<grid, kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs,
+                                                           dfb, f_in, unit, e1_io, e2bar, ubar); NN_LAUNCHED(1);
+    }
+    else {
+        k_pair_bwd_gather<false><<<grid, kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs,
+                                                            dfb, f_in, unit, e1_io, e2bar, ubar); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("pair_bwd_gather");
+    return 0;
+}
+int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* Wet,
+                               float* mbar_io, float* rbf_bar, cudaStream_t s) {
+    if (nl->cap_pairs <= 0) return 0;
+    k_pair_bwd_message<<<grid_for_rows(nl->cap_pairs), kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS,
+                                                                          nl->cap_pairs, abar, mn, rbf, Wet, mbar_io, rbf_bar); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("pair_bwd_message");
+    return 0;
+}
+int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
+                                 float* mnbar, float* fbar_new, bool first, cudaStream_t s) {
+    const int N = nl->n_atoms;
+    if (N <= 0) return 0;
+    int grid = nn_ceil_div(N, kWarps);
+    if (first) {
+        k_node_aggregate_bwd<true><<<grid, kThreads, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+    }
+    else {
+        k_node_aggregate_bwd<false><<<grid, kThreads, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("node_aggregate_bwd");
+    return 0;
+}

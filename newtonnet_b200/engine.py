@@ -1,0 +1,271 @@
+"""Host driver of the CUDA path: neighbour list, weight pack, one-call evaluation.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in
+libnewtonnet_b200.so (include/newtonnet_b200.h).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f'newtonnet_b200: `{name}` must be a CUDA tensor - this package has no CPU fallback '
+                           f'(use the reference implementation or oracle/ for CPU).')
+
+
+class WeightPack:
+    """fp32 device copies of the reference parameters in both orientations (nn_weights)."""
+
+    def __init__(self, state, cutoff, device):
+        """`state`: mapping with the reference's parameter names -> tensors."""
+        self.keep = []
+        dev = device
+
+        def f32(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self.keep.append(t)
+            return t
+
+        def both(t):
+            w = f32(t)
+            wt = f32(t.detach().t())
+            return w.data_ptr(), wt.data_ptr()
+
+        w = L.Weights()
+        n_layers = 1 + max(int(k.split('.')[1]) for k in state if k.startswith('interaction_layers.'))
+        if n_layers > L.NN_MAX_LAYERS:
+            raise ValueError(f'n_interactions={n_layers} > {L.NN_MAX_LAYERS}')
+        emb = state['embedding_layers.node_embedding.weight']
+        if emb.shape[1] != L.NN_F:
+            raise NotImplementedError(f'kernels are specialised for n_features={L.NN_F}, got {emb.shape[1]}')
+        freq = state['embedding_layers.edge_embedding.embedding.frequencies']
+        if freq.numel() != L.NN_NB:
+            raise NotImplementedError(f'kernels are specialised for n_basis={L.NN_NB}, got {freq.numel()}')
+        w.n_layers = n_layers
+        w.cutoff = float(cutoff)
+        w.embedding = f32(emb).data_ptr()
+        w.frequencies = f32(freq).data_ptr()
+        for l in range(n_layers):
+            k = f'interaction_layers.{l}.'
+            if (k + 'layer_norm.weight') in state:
+                raise NotImplementedError('layer_norm=True is not supported by the CUDA path yet')
+            lw = w.layer[l]
+            lw.W1, lw.W1t = both(state[k + 'message_nodepart.0.weight'])
+            lw.b1 = f32(state[k + 'message_nodepart.0.bias']).data_ptr()
+            lw.W2, lw.W2t = both(state[k + 'message_nodepart.2.weight'])
+            lw.b2 = f32(state[k + 'message_nodepart.2.bias']).data_ptr()
+            lw.We, lw.Wet = both(state[k + 'message_edgepart.weight'])
+            lw.U1, lw.U1t = both(state[k + 'equiv_message1.0.weight'])
+            lw.U2, lw.U2t = both(state[k + 'equiv_message1.2.weight'])
+            lw.V1, lw.V1t = both(state[k + 'equiv_message2.0.weight'])
+            lw.V2, lw.V2t = both(state[k + 'equiv_message2.2.weight'])
+            lw.Wu, lw.Wut = both(state[k + 'equiv_update.weight'])
+        h = 'output_layers.0.layers.'
+        hk = [k for k in state if k.endswith('layers.0.weight') and k.startswith('output_layers.')]
+        if hk:
+            h = hk[0][:-len('0.weight')]
+        idx = h.split('.')[1]
+        w.H1, w.H1t = both(state[h + '0.weight'])
+        w.hb1 = f32(state[h + '0.bias']).data_ptr()
+        w.H2, w.H2t = both(state[h + '2.weight'])
+        w.hb2 = f32(state[h + '2.bias']).data_ptr()
+        w.w3 = f32(state[h + '4.weight'].reshape(-1)).data_ptr()
+        w.hb3 = f32(state[h + '4.bias'].reshape(-1)).data_ptr()
+        w.scale = f32(state[f'scalers.{idx}.scale.weight'].reshape(-1)).data_ptr()
+        w.shift = f32(state[f'scalers.{idx}.shift.weight'].reshape(-1)).data_ptr()
+        self.struct = w
+        self.n_layers = n_layers
+        self.cutoff = float(cutoff)
+
+
+class NeighborList:
+    """Destination-sorted CSR + undirected pair list on the device (nn_nbr)."""
+
+    def __init__(self, engine, pos, cell, batch, cap_edges):
+        N, B = pos.shape[0], cell.shape[0]
+        dev = pos.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.pos, self.cell, self.batch = pos, cell, batch
+        self.n_atoms, self.n_systems = N, B
+        self.cap_edges = int(cap_edges)
+        self.cap_pairs = (self.cap_edges + 1) // 2
+        self.sys_ptr = torch.empty(B + 1, **i32)
+        self.row_ptr = torch.empty(N + 1, **i32)
+        self.pair_ptr = torch.empty(N + 1, **i32)
+        self.col = torch.empty(max(self.cap_edges, 1), **i32)
+        self.edge_pair = torch.empty(max(self.cap_edges, 1), **i32)
+        self.pair_i = torch.empty(max(self.cap_pairs, 1), **i32)
+        self.pair_j = torch.empty(max(self.cap_pairs, 1), **i32)
+        self.pair_disp = torch.empty(max(self.cap_pairs, 1), 3, dtype=torch.float32, device=dev)
+        self.status = torch.zeros(L.NN_STATUS_WORDS, **i32)
+        ws_bytes = engine.lib.nn_nbr_workspace_bytes(N, B)
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        s = L.Nbr()
+        s.n_atoms, s.n_systems = N, B
+        s.cap_edges, s.cap_pairs, s.cap_cells = self.cap_edges, self.cap_pairs, 2 * N + B
+        s.pos, s.cell, s.batch = pos.data_ptr(), cell.data_ptr(), batch.data_ptr()
+        s.sys_ptr, s.row_ptr, s.col = self.sys_ptr.data_ptr(), self.row_ptr.data_ptr(), self.col.data_ptr()
+        s.edge_pair, s.pair_ptr = self.edge_pair.data_ptr(), self.pair_ptr.data_ptr()
+        s.pair_i, s.pair_j, s.pair_disp = self.pair_i.data_ptr(), self.pair_j.data_ptr(), self.pair_disp.data_ptr()
+        s.status = self.status.data_ptr()
+        s.workspace, s.workspace_bytes = self.workspace.data_ptr(), ws_bytes
+        self.struct = s
+        self.n_edges = None   # known on the host after `check()`
+
+    def rebind(self, pos, cell, batch):
+        """Point the list at new input tensors of the same shapes (next MD step)."""
+        self.pos, self.cell, self.batch = pos, cell, batch
+        self.struct.pos, self.struct.cell, self.struct.batch = pos.data_ptr(), cell.data_ptr(), batch.data_ptr()
+
+    def check(self):
+        """Read the status words (one small D2H copy, synchronises the stream)."""
+        st = self.status.cpu().tolist()
+        if st[L.ST_BATCH_UNSORTED] == 1:
+            raise ValueError('batch must be non-decreasing with values in [0, n_systems)')
+        if st[L.ST_BATCH_UNSORTED] == 3:
+            raise ValueError('atomic numbers must be in [0, 118]')
+        if st[L.ST_BATCH_UNSORTED] == 2:
+            raise RuntimeError('internal error: asymmetric edge set')
+        if st[L.ST_SINGULAR_CELL]:
+            # the reference raises torch._C._LinAlgError from linalg.solve (representations.py:92)
+            raise RuntimeError('singular cell in a periodic batch (mixed periodic / non-periodic systems or '
+                               'partially periodic cells are not supported, as in the reference)')
+        if st[L.ST_ROW_OVERFLOW]:
+            raise RuntimeError(f'an atom has {st[L.ST_ROW_OVERFLOW]} neighbours (> {512})')
+        self.n_edges = st[L.ST_N_EDGES]
+        return st
+
+    def edge_index(self):
+        """[2,E] int64, reference order (i-major, j ascending)."""
+        if self.n_edges is None:
+            self.check()
+        out = torch.empty(2, self.n_edges, dtype=torch.int64, device=self.pos.device)
+        if self.n_edges:
+            lib = L.load()
+            L.check(lib.nn_nbr_edge_index(C.byref(self.struct), out.data_ptr(), self.n_edges, _stream()), 'nn_nbr_edge_index')
+        return out
+
+
+class Engine:
+    """Per-device driver.  Keeps capacities and workspaces between calls so a steady-state evaluation
+    allocates nothing and synchronises once (the status read that accompanies the results)."""
+
+    HEADROOM = 1.08
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('newtonnet_b200 runs on CUDA devices only (no CPU fallback)')
+        self.lib = L.load()
+        self._nl = None
+        self._ws = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ neighbour list
+    def neighbor_list(self, pos, cell, batch, cutoff):
+        for t, n in ((pos, 'pos'), (cell, 'cell'), (batch, 'batch')):
+            _require_cuda(t, n)
+        pos = pos.detach().to(torch.float32).contiguous()
+        cell = cell.detach().to(torch.float32).contiguous().reshape(-1, 3, 3)
+        batch = batch.to(torch.int64).contiguous()
+        N, B = pos.shape[0], cell.shape[0]
+        nl = self._nl
+        reuse = nl is not None and nl.n_atoms == N and nl.n_systems == B and nl.pos.device == pos.device
+        s = _stream()
+        if reuse:
+            nl.rebind(pos, cell, batch)
+            nl.n_edges = None
+            L.check(self.lib.nn_nbr_count(C.byref(nl.struct), cutoff, s), 'nn_nbr_count')
+            L.check(self.lib.nn_nbr_fill(C.byref(nl.struct), cutoff, s), 'nn_nbr_fill')
+            return nl   # overflow (if any) is detected by the caller's status check -> `grow`
+        probe = NeighborList(self, pos, cell, batch, cap_edges=0)
+        L.check(self.lib.nn_nbr_count(C.byref(probe.struct), cutoff, s), 'nn_nbr_count')
+        st = probe.check()
+        return self._build_with_capacity(pos, cell, batch, cutoff, st[L.ST_N_EDGES])
+
+    def _build_with_capacity(self, pos, cell, batch, cutoff, n_edges):
+        cap = int(n_edges * self.HEADROOM) + 64
+        cap += cap % 2
+        nl = NeighborList(self, pos, cell, batch, cap_edges=cap)
+        s = _stream()
+        L.check(self.lib.nn_nbr_count(C.byref(nl.struct), cutoff, s), 'nn_nbr_count')
+        L.check(self.lib.nn_nbr_fill(C.byref(nl.struct), cutoff, s), 'nn_nbr_fill')
+        self._nl = nl
+        return nl
+
+    def grow(self, nl, cutoff, needed):
+        return self._build_with_capacity(nl.pos, nl.cell, nl.batch, cutoff, needed)
+
+    # ------------------------------------------------------------------ evaluation
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != self.device:
+            self._ws = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def evaluate(self, nl, weights, z, want_forces=True, want_virial=False, want_nodes=False):
+        _require_cuda(z, 'z')
+        z = z.to(torch.int64).contiguous()
+        N, B = nl.n_atoms, nl.n_systems
+        dev = nl.pos.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = {'energy': torch.empty(B, **f32)}
+        bwd = want_forces or want_virial
+        if bwd:
+            out['forces'] = torch.empty(N, 3, **f32)
+        if want_virial:
+            out['virial'] = torch.empty(B, 3, 3, **f32)
+            out['stress'] = torch.empty(B, 3, 3, **f32)
+        if want_nodes:
+            out['atom_node'] = torch.empty(N, L.NN_F, **f32)
+            out['force_node'] = torch.empty(N, 3, L.NN_F, **f32)
+        nbytes = self.lib.nn_eval_workspace_bytes(N, B, nl.cap_pairs, weights.n_layers, int(bwd))
+        ws = self._workspace(nbytes)
+        a = L.EvalArgs()
+        a.nbr = C.pointer(nl.struct)
+        a.w = C.pointer(weights.struct)
+        a.z = z.data_ptr()
+        a.want_forces, a.want_virial = int(bwd), int(want_virial)
+        a.energy = out['energy'].data_ptr()
+        a.forces = L.ptr(out.get('forces'))
+        a.virial = L.ptr(out.get('virial'))
+        a.stress = L.ptr(out.get('stress'))
+        a.atom_node = L.ptr(out.get('atom_node'))
+        a.force_node = L.ptr(out.get('force_node'))
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(self.lib.nn_eval(C.byref(a), _stream()), 'nn_eval')
+        out['_z'] = z   # keep alive until the stream has consumed it
+        return out
+
+    def energy_forces(self, weights, z, pos, cell, batch, want_forces=True, want_virial=False, want_nodes=False):
+        """Neighbour list + evaluation + status check, regrowing capacities when needed."""
+        nl = self.neighbor_list(pos, cell, batch, weights.cutoff)
+        out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes)
+        st = nl.check()
+        if st[L.ST_EDGE_OVERFLOW]:
+            nl = self.grow(nl, weights.cutoff, max(st[L.ST_EDGE_OVERFLOW], st[L.ST_N_EDGES]))
+            out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes)
+            st = nl.check()
+            if st[L.ST_EDGE_OVERFLOW]:
+                raise RuntimeError('neighbour list capacity overflow after regrow')
+        out['_nl'] = nl
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device):
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    key = str(device)
+    if key not in _engines:
+        _engines[key] = Engine(device)
+    return _engines[key]

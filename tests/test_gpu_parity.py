@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the public NewtonNet API) against the CPU oracle
+and the committed golden vectors of the unmodified reference.
+
+Tolerances are those of BASELINE.json north_star: neighbour edge sets bit-exact, energies within 1e-5
+relative, forces within 1e-4 eV/A (fp32 kernels compared with the reference run in fp64).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_case, load_weights
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-5      # north_star: energies within 1e-5 relative
+F_ATOL = 1e-4      # north_star: forces within 1e-4 eV/A
+CASES_EF = ['aspirin1', 'aspirin100', 'mols24', 'mols_edge', 'mols256']
+CASES_PBC = ['water375', 'water81_smallL', 'water1029', 'water192_ortho_unwrapped', 'water_batch2']
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module', params=[0, 1], ids=['simt', 'tcgen05'])
+def backend(request):
+    from newtonnet_b200 import _lib
+    lib = _lib.load()
+    if request.param == 1:
+        probe = torch.zeros(128, 128, device=dev())
+        if not _tc_available(lib, probe):
+            pytest.skip('tcgen05 backend not built')
+    lib.nn_set_gemm_backend(request.param)
+    yield request.param
+    lib.nn_set_gemm_backend(0)
+
+
+def _tc_available(lib, probe):
+    from newtonnet_b200 import _lib as L
+    a = L.GemmArgs()
+    y = torch.empty_like(probe)
+    a.X, a.B, a.Y, a.m = probe.data_ptr(), probe.data_ptr(), y.data_ptr(), 128
+    lib.nn_set_gemm_backend(1)
+    rc = lib.nn_gemm128(C.byref(a), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    lib.nn_set_gemm_backend(0)
+    return rc == 0
+
+
+def make_model(weights, props):
+    from newtonnet_b200.compat import model_from_state_dict
+    m = model_from_state_dict({k: torch.tensor(v) for k, v in weights.items()}, output_properties=props)
+    m = m.to(dev())
+    m.eval()
+    return m
+
+
+def run_model(model, d):
+    t = lambda a, dt=None: torch.tensor(a, device=dev()) if dt is None else torch.tensor(a, device=dev(), dtype=dt)
+    return model(t(d['z']), t(d['pos']), t(d['cell']), t(d['batch']))
+
+
+# ----------------------------------------------------------------------------- neighbour list (R2)
+@pytest.mark.parametrize('name', CASES_EF + CASES_PBC + ['water192_triclinic'])
+def test_edge_set_bit_exact(name):
+    """Same edges in the same order as the reference's dense search, and bit-identical displacements."""
+    from newtonnet_b200.layers.representations import RadiusGraph
+    from oracle import newtonnet_oracle as O
+    d, _ = load_case(name)
+    ei, disp = RadiusGraph(5.0)(torch.tensor(d['pos'], device=dev()), torch.tensor(d['cell'], device=dev()),
+                                torch.tensor(d['batch'], device=dev()))
+    assert ei.dtype == torch.int64
+    if name == 'water192_triclinic':
+        # general cells: same formula, fp32 inverse instead of LAPACK LU ("parity unpinned" in SURVEY 8a R2);
+        # the edge SET still has to agree with the reference on this fixture.
+        got = set(map(tuple, ei.cpu().numpy().T.tolist()))
+        ref = set(map(tuple, d['ref32_edge_index'].T.tolist()))
+        assert got == ref
+        return
+    assert np.array_equal(ei.cpu().numpy(), d['ref32_edge_index'])
+    _, dref = O.radius_graph_dense(torch.tensor(d['pos']), torch.tensor(d['cell']), torch.tensor(d['batch']))
+    assert np.array_equal(disp.cpu().numpy(), dref.numpy())
+
+
+def test_edge_set_large_box_and_batch():
+    """C3 (3,000-atom water box) and a 512-molecule C2-shaped batch against the cell-list oracle."""
+    from newtonnet_b200.layers.representations import RadiusGraph
+    from oracle import newtonnet_oracle as O
+    for z, pos, cell, batch in (O.water_box(10), O.molecule_batch(512, seed=3)):
+        ei, disp = RadiusGraph(5.0)(torch.tensor(pos, device=dev()), torch.tensor(cell, device=dev()),
+                                    torch.tensor(batch, device=dev()))
+        ref_ei, ref_d = O.radius_graph_cell_list(pos, cell, batch)
+        assert np.array_equal(ei.cpu().numpy(), ref_ei)
+        assert np.array_equal(disp.cpu().numpy(), ref_d)
+
+
+def test_neighbor_list_errors():
+    from newtonnet_b200.layers.representations import RadiusGraph
+    pos = torch.rand(8, 3, device=dev())
+    with pytest.raises(ValueError):      # unsorted batch
+        RadiusGraph(5.0)(pos, torch.zeros(2, 3, 3, device=dev()), torch.tensor([0, 1, 0, 1, 0, 1, 0, 1], device=dev()))
+    cell = torch.zeros(1, 3, 3, device=dev()); cell[0, 0, 0] = 10.0      # partially periodic -> singular
+    with pytest.raises(RuntimeError, match='singular'):
+        RadiusGraph(5.0)(pos, cell, torch.zeros(8, dtype=torch.long, device=dev()))
+
+
+# ----------------------------------------------------------------------------- dense contraction
+def _gemm(lib, X, B, pro=0, epi=0, bias=None, aux1=None, aux2=None, aux3=None, m_dev=None, mul=1, Y=None):
+    from newtonnet_b200 import _lib as L
+    a = L.GemmArgs()
+    Y = torch.empty_like(X) if Y is None else Y
+    a.X, a.B, a.Y = X.data_ptr(), B.data_ptr(), Y.data_ptr()
+    a.bias, a.aux1, a.aux2, a.aux3 = L.ptr(bias), L.ptr(aux1), L.ptr(aux2), L.ptr(aux3)
+    a.m_dev, a.m_dev_mul, a.m, a.prologue, a.epilogue = L.ptr(m_dev), mul, X.shape[0], pro, epi
+    L.check(lib.nn_gemm128(C.byref(a), torch.cuda.current_stream().cuda_stream), 'nn_gemm128')
+    return Y
+
+
+@pytest.mark.parametrize('M', [1, 127, 128, 300, 3 * 211, 4099])
+def test_gemm128_variants(backend, M):
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device='cpu').manual_seed(M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev())
+    X, B, bias, aux = r(M, 128), r(128, 128) / 11.3, r(128), r(M, 128)
+    Xd, Bd = X.double(), B.double()
+    silu = lambda t: t * torch.sigmoid(t)
+    dsilu = lambda t: torch.sigmoid(t) * (1 + t * (1 - torch.sigmoid(t)))
+    tol = dict(rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(_gemm(lib, X, B, bias=bias).double(), Xd @ Bd + bias.double(), **tol)
+    torch.testing.assert_close(_gemm(lib, X, B).double(), Xd @ Bd, **tol)
+    torch.testing.assert_close(_gemm(lib, X, B, pro=L.PRO_SILU, bias=bias).double(), silu(Xd) @ Bd + bias.double(), **tol)
+    torch.testing.assert_close(_gemm(lib, X, B, epi=L.EPI_DSILU, aux1=aux).double(), (Xd @ Bd) * dsilu(aux.double()), **tol)
+    torch.testing.assert_close(_gemm(lib, X, B, epi=L.EPI_ADD, aux1=aux).double(), Xd @ Bd + aux.double(), **tol)
+    # in-place accumulate and in-place X == Y
+    acc = aux.clone()
+    _gemm(lib, X, B, epi=L.EPI_ADD, aux1=acc, Y=acc)
+    torch.testing.assert_close(acc.double(), Xd @ Bd + aux.double(), **tol)
+    xin = X.clone()
+    _gemm(lib, xin, B, epi=L.EPI_DSILU, aux1=aux, Y=xin)
+    torch.testing.assert_close(xin.double(), (Xd @ Bd) * dsilu(aux.double()), **tol)
+    if M % 3 == 0:
+        n = M // 3
+        abar, fbar, gg = r(n, 128), r(M, 128), r(M, 128)
+        want = (Xd * abar.double().repeat_interleave(3, 0)) @ Bd + fbar.double() + abar.double().repeat_interleave(3, 0) * gg.double()
+        got = _gemm(lib, X, B, pro=L.PRO_ROWSCALE3, epi=L.EPI_EQUIV_BWD, aux1=fbar, aux2=abar, aux3=gg)
+        torch.testing.assert_close(got.double(), want, **tol)
+    # device-side row count smaller than the launch capacity: rows beyond it are untouched
+    if M > 130:
+        cnt = torch.tensor([M - 100], dtype=torch.int32, device=dev())
+        Y = torch.full_like(X, 7.0)
+        _gemm(lib, X, B, m_dev=cnt, Y=Y)
+        torch.testing.assert_close(Y[:M - 100].double(), (Xd @ Bd)[:M - 100], **tol)
+        assert bool((Y[M - 100:] == 7.0).all())
+
+
+# ----------------------------------------------------------------------------- edge features (R3-R6)
+def test_edge_embedding_matches_oracle():
+    from newtonnet_b200.layers.representations import EdgeEmbedding
+    from oracle import newtonnet_oracle as O
+    d, w = load_case('water375')
+    emb = EdgeEmbedding(5.0, 20).to(dev())
+    rbf, unit, ei = emb(torch.tensor(d['pos'], device=dev()), torch.tensor(d['cell'], device=dev()),
+                        torch.tensor(d['batch'], device=dev()))
+    sd = O.as_torch_sd(w, torch.float64)
+    r64, u64, e64 = O.edge_embedding(sd, torch.tensor(d['pos']).double(), torch.tensor(d['cell']).double(),
+                                     torch.tensor(d['batch']))
+    assert np.array_equal(ei.cpu().numpy(), e64.numpy())
+    assert np.abs(rbf.cpu().double().numpy() - r64.numpy()).max() < 2e-6
+    assert np.abs(unit.cpu().double().numpy() - u64.numpy()).max() < 1e-6
+
+
+# ----------------------------------------------------------------------------- full path (R0-R10, B)
+@pytest.mark.parametrize('name', CASES_EF)
+def test_energy_forces_match_reference(backend, name):
+    d, w = load_case(name)
+    out = run_model(make_model(w, ['energy', 'gradient_force']), d)
+    e = out.energy.cpu().double().numpy(); f = out.gradient_force.cpu().double().numpy()
+    assert np.abs(e - d['ref64_energy']).max() <= E_RTOL * max(1.0, np.abs(d['ref64_energy']).max())
+    np.testing.assert_allclose(e, d['ref64_energy'], rtol=E_RTOL, atol=1e-4)
+    assert np.abs(f - d['ref64_forces']).max() < F_ATOL
+    assert np.array_equal(out.edge_index.cpu().numpy(), d['ref32_edge_index'])
+    if 'ref64_atom_node' in d:
+        assert np.abs(out.atom_node.cpu().double().numpy() - d['ref64_atom_node']).max() < 1e-4
+        assert np.abs(out.force_node.cpu().double().numpy() - d['ref64_force_node']).max() < 1e-4
+
+
+@pytest.mark.parametrize('name', CASES_PBC + ['water192_triclinic'])
+def test_periodic_energy_forces_stress_match_reference(backend, name):
+    d, w = load_case(name)
+    out = run_model(make_model(w, ['energy', 'gradient_force', 'stress', 'virial']), d)
+    e = out.energy.cpu().double().numpy(); f = out.gradient_force.cpu().double().numpy()
+    np.testing.assert_allclose(e, d['ref64_energy'], rtol=E_RTOL, atol=1e-4)
+    assert np.abs(f - d['ref64_forces']).max() < F_ATOL
+    s = out.stress.cpu().double().numpy(); v = out.virial.cpu().double().numpy()
+    assert np.abs(v - d['ref64_virial']).max() < 1e-4 * max(1.0, np.abs(d['ref64_virial']).max())
+    assert np.abs(s - d['ref64_stress']).max() < 1e-4 * np.abs(d['ref64_stress']).max() + 1e-8
+
+
+def test_known_answer_md_traj(backend):
+    """The reference's own trajectory scripts/md17_md/md.traj (201 frames, fp32 calculator on CUDA)."""
+    kat = np.load(f'{GOLDEN}/md17_kat.npz')
+    w = load_weights('md17')
+    nf = kat['positions'].shape[0]
+    d = dict(z=np.tile(kat['numbers'], nf), pos=kat['positions'].reshape(-1, 3).astype(np.float32),
+             cell=np.zeros((nf, 3, 3), np.float32), batch=np.repeat(np.arange(nf), 21))
+    out = run_model(make_model(w, ['energy', 'gradient_force']), d)
+    e = out.energy.cpu().double().numpy(); f = out.gradient_force.cpu().double().numpy().reshape(nf, 21, 3)
+    assert abs(e[0] - (-17591.8262)) < 0.02            # scripts/md17_md/md.log:2
+    assert np.abs(e / kat['energy'] - 1).max() < E_RTOL
+    assert np.abs(e - kat['energy']).max() < 8e-3      # a few fp32 ulps at 1.76e4 eV
+    assert np.abs(f - kat['forces']).max() < F_ATOL
+
+
+def test_c3_water_box_against_oracle(backend):
+    """3,000-atom periodic water box (config 3): edges from the cell-list oracle, E/F/stress from the
+    analytic fp64 oracle."""
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.water_box(10)
+    w = load_weights('seed0')
+    ei, disp = O.radius_graph_cell_list(pos, cell, batch)
+    ref = O.forward_analytic(w, z, pos, cell, batch, edge_index=ei, disp=disp)
+    out = run_model(make_model(w, ['energy', 'gradient_force', 'stress']), dict(z=z, pos=pos, cell=cell, batch=batch))
+    assert np.array_equal(out.edge_index.cpu().numpy(), ei)
+    np.testing.assert_allclose(out.energy.cpu().double().numpy(), ref['energy'], rtol=E_RTOL)
+    assert np.abs(out.gradient_force.cpu().double().numpy() - ref['forces']).max() < F_ATOL
+    assert np.abs(out.stress.cpu().double().numpy() - ref['stress']).max() < 1e-4 * np.abs(ref['stress']).max()
+
+
+def test_full_size_batch_properties(backend):
+    """Config 2 at full size (4,096 molecules, ~140k atoms): size-independent properties -
+    determinism, zero net force per molecule, invariance under a per-molecule rigid translation and
+    under molecule reordering, and agreement with the oracle on a 64-molecule sample."""
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.molecule_batch(4096, seed=1)
+    w = load_weights('seed0')
+    model = make_model(w, ['energy', 'gradient_force'])
+    d = dict(z=z, pos=pos, cell=cell, batch=batch)
+    o1 = run_model(model, d); e1 = o1.energy.clone(); f1 = o1.gradient_force.clone()
+    o2 = run_model(model, d)
+    assert torch.equal(e1, o2.energy) and torch.equal(f1, o2.gradient_force)        # deterministic
+    net = torch.zeros(4096, 3, device=dev(), dtype=torch.float64).index_add_(0, torch.tensor(batch, device=dev()), f1.double())
+    assert float(net.abs().max()) < 1e-3
+    shift = np.random.default_rng(0).uniform(-3, 3, (4096, 3)).astype(np.float32)
+    o3 = run_model(model, dict(z=z, pos=pos + shift[batch], cell=cell, batch=batch))
+    assert float((o3.energy - e1).abs().max()) < 1e-3 and float((o3.gradient_force - f1).abs().max()) < 2e-4
+    # oracle on the first 64 molecules
+    n = int((batch < 64).sum())
+    ref = O.forward(w, z[:n], pos[:n], cell[:64], batch[:n], dtype=torch.float64)
+    np.testing.assert_allclose(e1[:64].cpu().double().numpy(), ref['energy'], rtol=E_RTOL, atol=1e-4)
+    assert np.abs(f1[:n].cpu().double().numpy() - ref['forces']).max() < F_ATOL
+
+
+def test_capacity_regrow_and_reuse():
+    """Same atom count, denser second call: the cached capacity overflows and is regrown transparently."""
+    from oracle import newtonnet_oracle as O
+    w = load_weights('seed0')
+    model = make_model(w, ['energy', 'gradient_force'])
+    z, pos, cell, batch = O.water_box(6)
+    o1 = run_model(model, dict(z=z, pos=pos, cell=cell, batch=batch))
+    n1 = o1.edge_index.shape[1]
+    pos2 = (pos * 0.8).astype(np.float32); cell2 = (cell * 0.8).astype(np.float32)
+    o2 = run_model(model, dict(z=z, pos=pos2, cell=cell2, batch=batch))
+    ei, _ = O.radius_graph_cell_list(pos2, cell2, batch)
+    assert o2.edge_index.shape[1] == ei.shape[1] > 1.5 * n1
+    assert np.array_equal(o2.edge_index.cpu().numpy(), ei)
+    ref = O.forward_analytic(w, z, pos2, cell2, batch, edge_index=ei, disp=_)
+    assert np.abs(o2.gradient_force.cpu().double().numpy() - ref['forces']).max() < F_ATOL
+
+
+def test_head_order_and_energy_only():
+    d, w = load_case('aspirin1')
+    out = run_model(make_model(w, ['energy']), d)
+    assert not hasattr(out, 'gradient_force')
+    np.testing.assert_allclose(out.energy.cpu().double().numpy(), d['ref64_energy'], rtol=E_RTOL)
+    with pytest.raises(AttributeError):
+        run_model(make_model(w, ['gradient_force', 'energy']), d)
+
+
+# ----------------------------------------------------------------------------- calculator (R0 caller)
+class FakeAtoms:
+    """Duck-typed ase.Atoms (ase is not installed in the image)."""
+
+    def __init__(self, numbers, positions, cell=None, pbc=False):
+        self.numbers = np.asarray(numbers); self.positions = np.asarray(positions, dtype=np.float64)
+        self.cell = np.zeros((3, 3)) if cell is None else np.asarray(cell, dtype=np.float64)
+        self.pbc = np.array([pbc] * 3 if isinstance(pbc, bool) else pbc)
+
+    def __len__(self):
+        return len(self.numbers)
+
+    def copy(self):
+        return FakeAtoms(self.numbers.copy(), self.positions.copy(), self.cell.copy(), self.pbc.copy())
+
+    def get_atomic_numbers(self):
+        return self.numbers
+
+    def get_positions(self, wrap=False):
+        if wrap and self.pbc.any():
+            frac = np.linalg.solve(self.cell.T, self.positions.T).T
+            frac[:, self.pbc] %= 1.0
+            return frac @ self.cell
+        return self.positions
+
+    def get_cell(self):
+        return self.cell
+
+    def get_pbc(self):
+        return self.pbc
+
+
+def test_ase_calculator(tmp_path):
+    from newtonnet_b200.compat import model_from_state_dict
+    from newtonnet_b200.utils.ase_interface import MLAseCalculator
+    kat = np.load(f'{GOLDEN}/md17_kat.npz')
+    w = load_weights('md17')
+    path = tmp_path / 'best_model.pt'
+    torch.save(model_from_state_dict({k: torch.tensor(v).double() for k, v in w.items()}), path)   # fp64 pickle like the shipped one
+    calc = MLAseCalculator(str(path), properties=['energy', 'forces'], device='cuda:0', precision='single')
+    for k in (0, 100, 200):
+        atoms = FakeAtoms(kat['numbers'], kat['positions'][k])
+        calc.calculate(atoms)
+        assert calc.results['energy'].shape == () and calc.results['forces'].shape == (21, 3)
+        assert abs(float(calc.results['energy']) / kat['energy'][k] - 1) < E_RTOL
+        assert np.abs(calc.results['forces'] - kat['forces'][k]).max() < F_ATOL
+    calc.calculate([FakeAtoms(kat['numbers'], kat['positions'][k]) for k in range(4)])
+    assert calc.results['energy'].shape == (4,) and calc.results['forces'].shape == (4, 21, 3)
+    # periodic system with stress, Voigt order [xx,yy,zz,yz,xz,xy]
+    d, ws = load_case('water375')
+    torch.save(model_from_state_dict({k: torch.tensor(v) for k, v in ws.items()}), path)
+    calc = MLAseCalculator(str(path), properties=['energy', 'forces', 'stress'], device='cuda:0')
+    calc.calculate(FakeAtoms(d['z'], d['pos'], d['cell'][0], True))
+    s = d['ref64_stress'][0]
+    voigt = np.array([s[0, 0], s[1, 1], s[2, 2], s[1, 2], s[0, 2], s[0, 1]])
+    assert calc.results['stress'].shape == (6,)
+    assert np.abs(calc.results['stress'] - voigt).max() < 1e-4 * np.abs(voigt).max()
+    assert np.abs(calc.results['forces'] - d['ref64_forces']).max() < F_ATOL

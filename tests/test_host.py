@@ -1,0 +1,104 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the module mirror has the
+reference's parameter names, reference checkpoints convert.  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_weights
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from newtonnet_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, 'include', 'newtonnet_b200.h')).read()
+    declared = set(re.findall(r'^NN_API [\w\s\*]+?\b(nn_\w+)\(', hdr, flags=re.M))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.nn_version() >= 100
+    assert lib.nn_get_gemm_backend() in (0, 1)
+    # struct layouts agree with the header (sizes computed independently with the C compiler rules)
+    import ctypes as C
+    assert C.sizeof(_lib.LayerWeights) == 18 * 8
+    assert C.sizeof(_lib.Weights) == 8 + 2 * 8 + 8 * 18 * 8 + 10 * 8
+    assert C.sizeof(_lib.Nbr) == 5 * 4 + 4 + 13 * 8 + 8
+    assert C.sizeof(_lib.GemmArgs) == 8 * 8 + 4 * 4
+    assert lib.nn_nbr_workspace_bytes(1000, 4) > 0
+    assert lib.nn_eval_workspace_bytes(1000, 4, 30000, 3, 1) > lib.nn_eval_workspace_bytes(1000, 4, 30000, 3, 0)
+
+
+def test_no_cpu_fallback():
+    from newtonnet_b200.models import NewtonNet
+    m = NewtonNet(output_properties=['energy', 'gradient_force'])
+    m.eval()
+    z = torch.tensor([8, 1, 1]); pos = torch.rand(3, 3); cell = torch.zeros(1, 3, 3); batch = torch.zeros(3, dtype=torch.long)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(z, pos, cell, batch)
+
+
+def test_state_dict_keys_match_reference():
+    from newtonnet_b200.models import NewtonNet
+    m = NewtonNet(output_properties=['energy', 'gradient_force'])
+    ref = load_weights('seed0')
+    sd = m.state_dict()
+    assert set(sd) == set(ref)
+    assert all(tuple(sd[k].shape) == ref[k].shape for k in ref)
+    assert sum(v.numel() for v in sd.values()) == 401155
+    # frequencies are fp32(n*pi) exactly as the reference creates them (representations.py:220)
+    assert np.array_equal(sd['embedding_layers.edge_embedding.embedding.frequencies'].numpy(),
+                          ref['embedding_layers.edge_embedding.embedding.frequencies'])
+
+
+def test_factories_and_unsupported_heads():
+    from newtonnet_b200.layers import get_activation_by_string, get_precision_by_string, get_scaler_by_string
+    from newtonnet_b200.models import NewtonNet, get_aggregator_by_string, get_output_by_string
+    assert isinstance(get_activation_by_string('swish'), torch.nn.SiLU)
+    with pytest.raises(NotImplementedError):
+        get_activation_by_string('relu')
+    assert get_precision_by_string('single') is torch.float32
+    with pytest.raises(ValueError):
+        get_precision_by_string('bf16')
+    assert get_scaler_by_string('energy').scale is not None and get_scaler_by_string('stress').scale is None
+    for key in ('gradient_force', 'stress', 'virial'):
+        get_output_by_string(key); get_aggregator_by_string(key)
+    for key in ('charge', 'hessian', 'bec', 'direct_force'):
+        with pytest.raises(NotImplementedError):
+            get_output_by_string(key, 128, torch.nn.SiLU())
+    with pytest.raises(NotImplementedError):
+        NewtonNet(output_properties=['charge', 'energy'])
+    m = NewtonNet(output_properties=['energy', 'gradient_force'])
+    assert m.embedding_layers.requires_dr is True
+    m.eval()
+    assert m.output_layers[1].create_graph is False
+    m.train()
+    assert m.output_layers[1].create_graph is True
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/scripts/md17_model/training_1/models/best_model.pt'),
+                    reason='reference checkpoint only exists in the build container')
+def test_shipped_legacy_checkpoint_loads():
+    from newtonnet_b200.compat import load_model
+    m = load_model('/root/reference/scripts/md17_model/training_1/models/best_model.pt', map_location='cpu')
+    assert m.output_properties == ['energy', 'gradient_force'] and m.cutoff == 5.0
+    w = load_weights('md17')
+    sd = m.state_dict()
+    assert set(sd) == set(w)
+    assert all(np.array_equal(sd[k].float().numpy(), w[k]) for k in w)
+
+
+def test_pickled_mirror_module_round_trip(tmp_path):
+    """A whole-module pickle (the reference's checkpoint format, trainer.py:219) of the mirror loads back."""
+    from newtonnet_b200.compat import load_model, model_from_state_dict
+    w = load_weights('seed0')
+    m = model_from_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    p = tmp_path / 'model.pt'
+    torch.save(m, p)
+    m2 = load_model(str(p), map_location='cpu')
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    torch.save(m.state_dict(), p)
+    m3 = load_model(str(p), map_location='cpu')
+    assert set(m3.state_dict()) == set(w)
