@@ -72,17 +72,23 @@ NN_API int nn_profile_enable(int on);
 NN_API int nn_profile_collect(float* ms_per_stage, int* n_per_stage, int n_stages);
 
 /* ------------------------------------------------------------------ weights
- * Pointers to fp32 device copies of the reference parameters (names: SURVEY.md section 8b).  `W` is the
- * torch layout [out, in]; `Wt` its transpose [in, out].  Forward products x @ W^T read Wt, backward
- * products g @ W read W.
+ * fp32 device copies of the reference parameters (names: SURVEY.md section 8b).  A 128x128 matrix is
+ * passed as `w` (torch layout [out, in]) and `wt` (its transpose [in, out]): forward products
+ * x @ W^T use B = wt, reverse-sweep products g @ W use B = w (B is always row-major [K, N]).
+ * `w_img` / `wt_img` are the tensor-core operand images of w / wt written by nn_gemm128_prepare_b
+ * (NULL = tensor-core backend unavailable for this matrix).
  */
 typedef struct {
-    const float *W1, *W1t, *b1;     /* interaction_layers.l.message_nodepart.0 */
-    const float *W2, *W2t, *b2;     /* interaction_layers.l.message_nodepart.2 */
+    const float *w, *wt, *w_img, *wt_img;
+} nn_mat;
+
+typedef struct {
+    nn_mat W1; const float* b1;     /* interaction_layers.l.message_nodepart.0 */
+    nn_mat W2; const float* b2;     /* interaction_layers.l.message_nodepart.2 */
     const float *We, *Wet;          /* message_edgepart.weight [F, nb] and its transpose [nb, F] */
-    const float *U1, *U1t, *U2, *U2t; /* equiv_message1.{0,2}.weight */
-    const float *V1, *V1t, *V2, *V2t; /* equiv_message2.{0,2}.weight */
-    const float *Wu, *Wut;          /* equiv_update.weight */
+    nn_mat U1, U2;                  /* equiv_message1.{0,2}.weight */
+    nn_mat V1, V2;                  /* equiv_message2.{0,2}.weight */
+    nn_mat Wu;                      /* equiv_update.weight */
 } nn_layer_weights;
 
 typedef struct {
@@ -91,8 +97,8 @@ typedef struct {
     const float* embedding;         /* embedding_layers.node_embedding.weight [119, F] */
     const float* frequencies;       /* embedding_layers.edge_embedding.embedding.frequencies [nb] */
     nn_layer_weights layer[NN_MAX_LAYERS];
-    const float *H1, *H1t, *hb1;    /* output_layers.k.layers.0 */
-    const float *H2, *H2t, *hb2;    /* output_layers.k.layers.2 */
+    nn_mat H1; const float* hb1;    /* output_layers.k.layers.0 */
+    nn_mat H2; const float* hb2;    /* output_layers.k.layers.2 */
     const float *w3, *hb3;          /* output_layers.k.layers.4  ([1,F], [1]) */
     const float *scale, *shift;     /* scalers.k.{scale,shift}.weight [119] */
 } nn_weights;
@@ -137,19 +143,29 @@ NN_API int nn_nbr_edge_index(const nn_nbr* nl, int64_t* edge_index, int64_t n_ed
  * calls of models/newtonnet.py:209,218,222,230 and models/output.py:98-100 and their autograd
  * transposes.  `m_dev` (optional) holds the row count on the device; then `m` is the launch capacity.
  */
-enum { NN_PRO_NONE = 0, NN_PRO_SILU = 1, NN_PRO_ROWSCALE3 = 2 };
-enum { NN_EPI_BIAS = 0, NN_EPI_DSILU = 1, NN_EPI_ADD = 2, NN_EPI_EQUIV_BWD = 3 };
+/* prologues: NONE; SILU: silu(X); ROWSCALE3: X[r] * aux2[r/3]; SILU_SAVE: silu(X) and additionally
+ * aux_out = silu'(X) (aux_out may alias X: the reverse sweep then needs no transcendental).
+ * epilogues: BIAS: + bias (may be NULL); DSILU: * silu'(aux1); ADD: + aux1; EQUIV_BWD: + aux1 + aux2[r/3]*aux3;
+ * MUL: * aux1. */
+enum { NN_PRO_NONE = 0, NN_PRO_SILU = 1, NN_PRO_ROWSCALE3 = 2, NN_PRO_SILU_SAVE = 3 };
+enum { NN_EPI_BIAS = 0, NN_EPI_DSILU = 1, NN_EPI_ADD = 2, NN_EPI_EQUIV_BWD = 3, NN_EPI_MUL = 4 };
+#define NN_B_IMAGE_FLOATS (2 * 128 * 128)
 typedef struct {
     const float* X; const float* B; float* Y;
+    const float* B_img;             /* operand image of B from nn_gemm128_prepare_b (tensor-core backend) */
     const float* bias;              /* NN_EPI_BIAS: [128] or NULL */
-    const float* aux1;              /* DSILU: pre-activation [M,128]; ADD: addend [M,128]; EQUIV_BWD: fbar [M,128] */
+    const float* aux1;              /* DSILU: pre-activation; ADD: addend; MUL: factor; EQUIV_BWD: fbar  (all [M,128]) */
     const float* aux2;              /* ROWSCALE3 / EQUIV_BWD: abar [M/3,128] */
     const float* aux3;              /* EQUIV_BWD: g [M,128] */
+    float* aux_out;                 /* SILU_SAVE: receives silu'(X) [M,128] */
     const int32_t* m_dev; int32_t m_dev_mul;   /* rows = m_dev[0] * m_dev_mul when m_dev != NULL */
     int32_t m;
     int32_t prologue, epilogue;
 } nn_gemm_args;
 NN_API int nn_gemm128(const nn_gemm_args* a, void* stream);
+/* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo
+ * parts, laid out as UMMA K-major 128B-swizzled blocks; `image` holds NN_B_IMAGE_FLOATS floats. */
+NN_API int nn_gemm128_prepare_b(const float* B, float* image, void* stream);
 /* backend for nn_gemm128 and nn_eval: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 tensor cores. */
 NN_API int nn_set_gemm_backend(int backend);
 NN_API int nn_get_gemm_backend(void);

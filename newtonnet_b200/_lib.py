@@ -13,25 +13,29 @@ NN_F = 128
 NN_NB = 20
 NN_MAX_LAYERS = 8
 NN_STATUS_WORDS = 8
+NN_B_IMAGE_FLOATS = 2 * 128 * 128
 ST_EDGE_OVERFLOW, ST_ROW_OVERFLOW, ST_BATCH_UNSORTED, ST_SINGULAR_CELL, ST_N_EDGES, ST_N_PAIRS, ST_N_CELLS = range(7)
 STAGES = ['nbr', 'geom', 'node_gemm', 'pair_gemm', 'message', 'aggregate', 'head', 'bwd_gather', 'bwd_message',
           'bwd_aggregate', 'force', 'other']
-PRO_NONE, PRO_SILU, PRO_ROWSCALE3 = 0, 1, 2
-EPI_BIAS, EPI_DSILU, EPI_ADD, EPI_EQUIV_BWD = 0, 1, 2, 3
+PRO_NONE, PRO_SILU, PRO_ROWSCALE3, PRO_SILU_SAVE = 0, 1, 2, 3
+EPI_BIAS, EPI_DSILU, EPI_ADD, EPI_EQUIV_BWD, EPI_MUL = 0, 1, 2, 3, 4
 
 _fp = C.c_void_p   # device pointers travel as integers
 
 
+class Mat(C.Structure):
+    _fields_ = [('w', _fp), ('wt', _fp), ('w_img', _fp), ('wt_img', _fp)]
+
+
 class LayerWeights(C.Structure):
-    _fields_ = [(n, _fp) for n in (
-        'W1', 'W1t', 'b1', 'W2', 'W2t', 'b2', 'We', 'Wet',
-        'U1', 'U1t', 'U2', 'U2t', 'V1', 'V1t', 'V2', 'V2t', 'Wu', 'Wut')]
+    _fields_ = [('W1', Mat), ('b1', _fp), ('W2', Mat), ('b2', _fp), ('We', _fp), ('Wet', _fp),
+                ('U1', Mat), ('U2', Mat), ('V1', Mat), ('V2', Mat), ('Wu', Mat)]
 
 
 class Weights(C.Structure):
     _fields_ = [('n_layers', C.c_int32), ('cutoff', C.c_float), ('embedding', _fp), ('frequencies', _fp),
-                ('layer', LayerWeights * NN_MAX_LAYERS)] + [(n, _fp) for n in (
-                    'H1', 'H1t', 'hb1', 'H2', 'H2t', 'hb2', 'w3', 'hb3', 'scale', 'shift')]
+                ('layer', LayerWeights * NN_MAX_LAYERS), ('H1', Mat), ('hb1', _fp), ('H2', Mat), ('hb2', _fp),
+                ('w3', _fp), ('hb3', _fp), ('scale', _fp), ('shift', _fp)]
 
 
 class Nbr(C.Structure):
@@ -42,7 +46,7 @@ class Nbr(C.Structure):
 
 
 class GemmArgs(C.Structure):
-    _fields_ = [('X', _fp), ('B', _fp), ('Y', _fp), ('bias', _fp), ('aux1', _fp), ('aux2', _fp), ('aux3', _fp),
+    _fields_ = [('X', _fp), ('B', _fp), ('Y', _fp), ('B_img', _fp), ('bias', _fp), ('aux1', _fp), ('aux2', _fp), ('aux3', _fp), ('aux_out', _fp),
                 ('m_dev', _fp), ('m_dev_mul', C.c_int32), ('m', C.c_int32), ('prologue', C.c_int32),
                 ('epilogue', C.c_int32)]
 
@@ -65,6 +69,7 @@ SYMBOLS = {
     'nn_nbr_fill': (C.c_int, [C.POINTER(Nbr), C.c_float, _fp]),
     'nn_nbr_edge_index': (C.c_int, [C.POINTER(Nbr), _fp, C.c_int64, _fp]),
     'nn_gemm128': (C.c_int, [C.POINTER(GemmArgs), _fp]),
+    'nn_gemm128_prepare_b': (C.c_int, [_fp, _fp, _fp]),
     'nn_set_gemm_backend': (C.c_int, [C.c_int]),
     'nn_get_gemm_backend': (C.c_int, []),
     'nn_eval_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

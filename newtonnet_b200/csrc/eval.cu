@@ -149,13 +149,22 @@ EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
 
 struct Gemm {
     cudaStream_t s; int rc = 0;
-    void run(const float* X, const float* B, float* Y, int m, int pro, int epi, const float* bias = nullptr,
+    // fwd(M): x @ M^T -> B = M.wt ; bwd(M): g @ M -> B = M.w
+    void fwd(const float* X, const nn_mat& M, float* Y, int m, int pro, int epi, const float* bias = nullptr,
              const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
-             const int* m_dev = nullptr, int mul = 1) {
+             const int* m_dev = nullptr) { run(X, M.wt, M.wt_img, Y, m, pro, epi, bias, aux1, aux2, aux3, m_dev); }
+    void bwd(const float* X, const nn_mat& M, float* Y, int m, int pro, int epi, const float* bias = nullptr,
+             const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
+             const int* m_dev = nullptr) { run(X, M.w, M.w_img, Y, m, pro, epi, bias, aux1, aux2, aux3, m_dev); }
+    void run(const float* X, const float* B, const float* B_img, float* Y, int m, int pro, int epi,
+             const float* bias = nullptr, const float* aux1 = nullptr, const float* aux2 = nullptr,
+             const float* aux3 = nullptr, const int* m_dev = nullptr, int mul = 1) {
         if (rc) return;
         ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
         nn_gemm_args a{};
-        a.X = X; a.B = B; a.Y = Y; a.bias = bias; a.aux1 = aux1; a.aux2 = aux2; a.aux3 = aux3;
+        // SILU_SAVE overwrites the pre-activation X with silu'(X) in place (X is not needed afterwards)
+        if (pro == NN_PRO_SILU_SAVE) a.aux_out = const_cast<float*>(X);
+        a.X = X; a.B = B; a.B_img = B_img; a.Y = Y; a.bias = bias; a.aux1 = aux1; a.aux2 = aux2; a.aux3 = aux3;
         a.m_dev = m_dev; a.m_dev_mul = mul; a.m = m; a.prologue = pro; a.epilogue = epi;
         rc = nn_gemm128_launch(a, s);
     }
@@ -186,6 +195,8 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
     EvalWs w = carve_eval(a->workspace, a->workspace_bytes, N, P, L, bwd);
     const int* np_dev = nl->status + NN_ST_N_PAIRS;
     Gemm g{s};
+    // with a reverse sweep the activation GEMMs leave silu'(pre) behind in place of pre
+    const int PRO_ACT = bwd ? NN_PRO_SILU_SAVE : NN_PRO_SILU;
 
     // ---- edge features (R3-R6) and embedding (R1)
     { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.unit, w.dist, s)); }
@@ -199,26 +210,26 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
         LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
-        g.run(a_cur, lw.W1t, b.pre, N, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
-        g.run(b.pre, lw.W2t, b.mn, N, NN_PRO_SILU, NN_EPI_BIAS, lw.b2);
+        g.fwd(a_cur, lw.W1, b.pre, N, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
+        g.fwd(b.pre, lw.W2, b.mn, N, PRO_ACT, NN_EPI_BIAS, lw.b2);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_MESSAGE, s); NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s)); }
-        g.run(b.msg, lw.U1t, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-        g.run(b.q1, lw.U2t, b.e1, P, NN_PRO_SILU, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.fwd(b.msg, lw.U1, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.fwd(b.q1, lw.U2, b.e1, P, PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
-            g.run(b.msg, lw.V1t, b.q2, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-            g.run(b.q2, lw.V2t, b.e2, P, NN_PRO_SILU, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+            g.fwd(b.msg, lw.V1, b.q2, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+            g.fwd(b.q2, lw.V2, b.e2, P, PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd(nl, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
-        g.run(b.f_out, lw.Wut, b.g, 3 * N, NN_PRO_NONE, NN_EPI_BIAS);
+        g.fwd(b.f_out, lw.Wu, b.g, 3 * N, NN_PRO_NONE, NN_EPI_BIAS);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, N, s)); }
     }
 
     // ---- energy head (R8, R9)
-    g.run(a_cur, W.H1t, w.h1pre, N, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
-    g.run(w.h1pre, W.H2t, w.h2pre, N, NN_PRO_SILU, NN_EPI_BIAS, W.hb2);
+    g.fwd(a_cur, W.H1, w.h1pre, N, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
+    g.fwd(w.h1pre, W.H2, w.h2pre, N, PRO_ACT, NN_EPI_BIAS, W.hb2);
     NN_TRY(g.rc);
     { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd(w.h2pre, W.w3, W.hb3, W.scale, W.shift, a->z, nl->sys_ptr, N, B, w.e_atom, a->energy, s)); }
     if (a->atom_node) cudaMemcpyAsync(a->atom_node, a_cur, (size_t)N * kF * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -228,8 +239,8 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
 
     // ---- reverse sweep (R10 / row B)
     { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_seed_launch(w.h2pre, W.w3, W.scale, a->z, N, w.tmpN, s)); }   // gh2
-    g.run(w.tmpN, W.H2, w.mnbar, N, NN_PRO_NONE, NN_EPI_DSILU, nullptr, w.h1pre);                    // gh1
-    g.run(w.mnbar, W.H1, w.abar, N, NN_PRO_NONE, NN_EPI_BIAS);                                       // abar
+    g.bwd(w.tmpN, W.H2, w.mnbar, N, NN_PRO_NONE, NN_EPI_MUL, nullptr, w.h1pre);                    // gh1
+    g.bwd(w.mnbar, W.H1, w.abar, N, NN_PRO_NONE, NN_EPI_BIAS);                                       // abar
     NN_TRY(g.rc);
     cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
     cudaMemsetAsync(w.rbf_bar, 0, (size_t)P * kNB * sizeof(float), s);
@@ -242,22 +253,22 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
         // dfb = fbar + abar*g + (abar*f_out) @ Wu
-        g.run(b.f_out, lw.Wu, dfb, 3 * N, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, fbar, w.abar, b.g);
+        g.bwd(b.f_out, lw.Wu, dfb, 3 * N, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, fbar, w.abar, b.g);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_BWD_GATHER, s); NN_TRY(nn_pair_bwd_gather_launch(nl, dfb, f_in, w.unit, b.e1, w.e2bar, w.ubar, first, s)); }
         // mbar = ((e1bar @ U2) * silu'(q1)) @ U1 + ((e2bar @ V2) * silu'(q2)) @ V1
-        g.run(b.e1, lw.U2, b.e1, P, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.q1, nullptr, nullptr, np_dev);
-        g.run(b.e1, lw.U1, w.mbar, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.bwd(b.e1, lw.U2, b.e1, P, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.q1, nullptr, nullptr, np_dev);
+        g.bwd(b.e1, lw.U1, w.mbar, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         if (!first) {
-            g.run(w.e2bar, lw.V2, w.e2bar, P, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.q2, nullptr, nullptr, np_dev);
-            g.run(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
+            g.bwd(w.e2bar, lw.V2, w.e2bar, P, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.q2, nullptr, nullptr, np_dev);
+            g.bwd(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, lw.Wet, w.mbar, w.rbf_bar, s)); }
         { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, w.mbar, b.mn, b.e2, dfb, w.mnbar, fbar, first, s)); }
         // abar += ((mnbar @ W2) * silu'(pre)) @ W1
-        g.run(w.mnbar, lw.W2, w.tmpN, N, NN_PRO_NONE, NN_EPI_DSILU, nullptr, b.pre);
-        g.run(w.tmpN, lw.W1, w.abar, N, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
+        g.bwd(w.mnbar, lw.W2, w.tmpN, N, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
+        g.bwd(w.tmpN, lw.W1, w.abar, N, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
         NN_TRY(g.rc);
         // fbar of the next (lower) layer was written into `fbar`; dfb is scratch again
     }

@@ -26,6 +26,9 @@ __device__ __forceinline__ float4 load_a(const nn_gemm_args& a, int grow, int k,
     float4 v = ld4(a.X + (size_t)grow * KTOT + k);
     if (PRO == NN_PRO_SILU) {
         v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+    } else if (PRO == NN_PRO_SILU_SAVE) {   // every X element is loaded by exactly one thread of one block
+        st4(a.aux_out + (size_t)grow * KTOT + k, make_float4(dsilu_f(v.x), dsilu_f(v.y), dsilu_f(v.z), dsilu_f(v.w)));
+        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
     } else if (PRO == NN_PRO_ROWSCALE3) {
         float4 s = ld4(a.aux2 + (size_t)(grow / 3) * KTOT + k);
         v = f4_mul(v, s);
@@ -42,6 +45,8 @@ __device__ __forceinline__ float4 epilogue(const nn_gemm_args& a, float4 acc, in
         acc.x *= dsilu_f(p.x); acc.y *= dsilu_f(p.y); acc.z *= dsilu_f(p.z); acc.w *= dsilu_f(p.w);
     } else if (EPI == NN_EPI_ADD) {
         acc = f4_add(acc, ld4(a.aux1 + (size_t)grow * BN + col));
+    } else if (EPI == NN_EPI_MUL) {
+        acc = f4_mul(acc, ld4(a.aux1 + (size_t)grow * BN + col));
     } else if (EPI == NN_EPI_EQUIV_BWD) {
         float4 fb = ld4(a.aux1 + (size_t)grow * BN + col);
         float4 ab = ld4(a.aux2 + (size_t)(grow / 3) * BN + col);
@@ -140,6 +145,8 @@ int nn_gemm128_simt_launch(const nn_gemm_args& a, cudaStream_t s) {
     NN_CASE(NN_PRO_NONE, NN_EPI_DSILU)
     NN_CASE(NN_PRO_NONE, NN_EPI_ADD)
     NN_CASE(NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD)
+    NN_CASE(NN_PRO_SILU_SAVE, NN_EPI_BIAS)
+    NN_CASE(NN_PRO_NONE, NN_EPI_MUL)
 #undef NN_CASE
     nn_set_error("nn_gemm128: unsupported prologue/epilogue combination %d/%d", a.prologue, a.epilogue);
     return -1;

@@ -293,7 +293,8 @@ k_nbr_count(const float* __restrict__ pos, const int64_t* __restrict__ batch, in
 __global__ void k_finish_count(const int* __restrict__ row_ptr, int N, int cap_edges, int* __restrict__ status) {
     int E = row_ptr[N];
     status[NN_ST_N_EDGES] = E;
-    status[NN_ST_N_PAIRS] = E / 2;
+    // on overflow the pair arrays are not (re)written: expose zero pairs so no kernel reads stale entries
+    status[NN_ST_N_PAIRS] = E > cap_edges ? 0 : E / 2;
     if (E > cap_edges) status[NN_ST_EDGE_OVERFLOW] = E;
 }
 

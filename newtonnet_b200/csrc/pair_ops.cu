@@ -123,13 +123,13 @@ k_edge_message_fwd(const int* __restrict__ pair_i, const int* __restrict__ pair_
 // a_out_i = a_i + sum_{e->i} m_p(e);  f_out_i[c] = f_i[c] + sum_{e->i} (s_e u_p[c] e1_p + e2_p * f_j[c])
 template <bool FIRST>
 __global__ void __launch_bounds__(kThreads)
-k_node_aggregate_fwd(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
-                     int N, const float* __restrict__ msg, const float* __restrict__ e1,
+k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                     const int* __restrict__ edge_pair, int N, const float* __restrict__ msg, const float* __restrict__ e1,
                      const float* __restrict__ e2, const float* __restrict__ unit, const float* __restrict__ a_in,
                      const float* __restrict__ f_in, float* __restrict__ a_out, float* __restrict__ f_out) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (i >= N) return;
+    if (i >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;   // overflow: row_ptr is ahead of col / edge_pair
     const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
     float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
     for (int e0 = r0; e0 < r1; e0 += 32) {
@@ -311,12 +311,12 @@ k_pair_bwd_message(const int* __restrict__ pair_i, const int* __restrict__ pair_
 // mnbar_k = sum_{e=(k,i)} t_p * mn_i ;  fbar_new_k[c] = dfb_k[c] + sum_{e=(k,i)} dfb_i[c] * e2_p
 template <bool FIRST>
 __global__ void __launch_bounds__(kThreads)
-k_node_aggregate_bwd(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
-                     int N, const float* __restrict__ t, const float* __restrict__ mn, const float* __restrict__ e2,
+k_node_aggregate_bwd(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                     const int* __restrict__ edge_pair, int N, const float* __restrict__ t, const float* __restrict__ mn, const float* __restrict__ e2,
                      const float* __restrict__ dfb, float* __restrict__ mnbar, float* __restrict__ fbar_new) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (k >= N) return;
+    if (k >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;
     const int r0 = row_ptr[k], r1 = row_ptr[k + 1];
     float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
     for (int e0 = r0; e0 < r1; e0 += 32) {
@@ -352,12 +352,12 @@ k_node_aggregate_bwd(const int* __restrict__ row_ptr, const int* __restrict__ co
 // reference's (unphysical but reproducible) extra term otherwise.  Each atom accumulates its forward
 // pairs; systems are summed in fp64 in fixed order.
 __global__ void __launch_bounds__(128)
-k_force_virial_atom(const int* __restrict__ row_ptr, const int* __restrict__ col, const int* __restrict__ edge_pair,
-                    int N, const float* __restrict__ G, const float* __restrict__ pair_disp,
+k_force_virial_atom(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                    const int* __restrict__ edge_pair, int N, const float* __restrict__ G, const float* __restrict__ pair_disp,
                     const float* __restrict__ pos, const int64_t* __restrict__ batch,
                     const SysMeta* __restrict__ meta, float* __restrict__ forces, float* __restrict__ vir_atom) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;
     const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
     float fx = 0.f, fy = 0.f, fz = 0.f;
     float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -494,11 +494,11 @@ extern "C" int nn_node_aggregate_fwd(const nn_nbr* nl, const float* msg, const f
     if (N <= 0) return 0;
     int grid = nn_ceil_div(N, kWarps);
     if (first_layer) {
-        k_node_aggregate_fwd<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+        k_node_aggregate_fwd<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
                                                                                 e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
     }
     else {
-        k_node_aggregate_fwd<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+        k_node_aggregate_fwd<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
                                                                                  e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("nn_node_aggregate_fwd");
@@ -532,7 +532,7 @@ extern "C" int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, f
     float* vir_atom = virial ? (float*)workspace : nullptr;
     NN_REQUIRE(!virial || workspace, "virial needs a workspace of n_atoms*9 floats");
     if (N > 0) {
-        k_force_virial_atom<<<nn_ceil_div(N, 128), 128, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, disp_bar,
+        k_force_virial_atom<<<nn_ceil_div(N, 128), 128, 0, s>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, disp_bar,
                                                                  nl->pair_disp, nl->pos, nl->batch, nn_nbr_sysmeta(nl),
                                                                  forces, vir_atom); NN_LAUNCHED(1);
     }
@@ -586,10 +586,10 @@ int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* 
     if (N <= 0) return 0;
     int grid = nn_ceil_div(N, kWarps);
     if (first) {
-        k_node_aggregate_bwd<true><<<grid, kThreads, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+        k_node_aggregate_bwd<true><<<grid, kThreads, 0, s>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
     }
     else {
-        k_node_aggregate_bwd<false><<<grid, kThreads, 0, s>>>(nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+        k_node_aggregate_bwd<false><<<grid, kThreads, 0, s>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("node_aggregate_bwd");
     return 0;

@@ -33,6 +33,22 @@ class WeightPack:
             self.keep.append(t)
             return t
 
+        lib = L.load()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def image(b):
+            img = torch.empty(L.NN_B_IMAGE_FLOATS, dtype=torch.float32, device=dev)
+            self.keep.append(img)
+            L.check(lib.nn_gemm128_prepare_b(b.data_ptr(), img.data_ptr(), stream), 'nn_gemm128_prepare_b')
+            return img.data_ptr()
+
+        def mat(dst, t):
+            """Both orientations of a [128,128] weight plus their tensor-core operand images."""
+            w = f32(t)
+            wt = f32(t.detach().t())
+            dst.w, dst.wt = w.data_ptr(), wt.data_ptr()
+            dst.w_img, dst.wt_img = image(w), image(wt)
+
         def both(t):
             w = f32(t)
             wt = f32(t.detach().t())
@@ -57,24 +73,24 @@ class WeightPack:
             if (k + 'layer_norm.weight') in state:
                 raise NotImplementedError('layer_norm=True is not supported by the CUDA path yet')
             lw = w.layer[l]
-            lw.W1, lw.W1t = both(state[k + 'message_nodepart.0.weight'])
+            mat(lw.W1, state[k + 'message_nodepart.0.weight'])
             lw.b1 = f32(state[k + 'message_nodepart.0.bias']).data_ptr()
-            lw.W2, lw.W2t = both(state[k + 'message_nodepart.2.weight'])
+            mat(lw.W2, state[k + 'message_nodepart.2.weight'])
             lw.b2 = f32(state[k + 'message_nodepart.2.bias']).data_ptr()
             lw.We, lw.Wet = both(state[k + 'message_edgepart.weight'])
-            lw.U1, lw.U1t = both(state[k + 'equiv_message1.0.weight'])
-            lw.U2, lw.U2t = both(state[k + 'equiv_message1.2.weight'])
-            lw.V1, lw.V1t = both(state[k + 'equiv_message2.0.weight'])
-            lw.V2, lw.V2t = both(state[k + 'equiv_message2.2.weight'])
-            lw.Wu, lw.Wut = both(state[k + 'equiv_update.weight'])
+            mat(lw.U1, state[k + 'equiv_message1.0.weight'])
+            mat(lw.U2, state[k + 'equiv_message1.2.weight'])
+            mat(lw.V1, state[k + 'equiv_message2.0.weight'])
+            mat(lw.V2, state[k + 'equiv_message2.2.weight'])
+            mat(lw.Wu, state[k + 'equiv_update.weight'])
         h = 'output_layers.0.layers.'
         hk = [k for k in state if k.endswith('layers.0.weight') and k.startswith('output_layers.')]
         if hk:
             h = hk[0][:-len('0.weight')]
         idx = h.split('.')[1]
-        w.H1, w.H1t = both(state[h + '0.weight'])
+        mat(w.H1, state[h + '0.weight'])
         w.hb1 = f32(state[h + '0.bias']).data_ptr()
-        w.H2, w.H2t = both(state[h + '2.weight'])
+        mat(w.H2, state[h + '2.weight'])
         w.hb2 = f32(state[h + '2.bias']).data_ptr()
         w.w3 = f32(state[h + '4.weight'].reshape(-1)).data_ptr()
         w.hb3 = f32(state[h + '4.bias'].reshape(-1)).data_ptr()
