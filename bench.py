@@ -209,7 +209,7 @@ def main_b200(args):
     lib = L.load()
     backend = args.backend
     if backend == 'auto':
-        backend = 'tc' if os.environ.get('NN_DEFAULT_BACKEND', 'simt') == 'tc' else 'simt'
+        backend = 'tc' if lib.nn_get_gemm_backend() == 1 else 'simt'
     lib.nn_set_gemm_backend(1 if backend == 'tc' else 0)
 
     K, W = args.steps, max(args.warmup, 3)

@@ -201,13 +201,14 @@ NN_API int nn_eval(const nn_eval_args* a, void* stream);
 /* ------------------------------------------------------------------ staged operators (also used by
  * nn_eval; exported for per-kernel parity tests and for the differentiable training path) */
 /* ScaledNorm + PolynomialCutoff * RadialBessel, representations.py:129-131,166-169,233,41:
- * per pair d, u = disp/d, rbf[nb] = env(d/rc) * sin(f_n d/rc) / (d/rc). */
+ * per pair d, u = disp/d, x = d/rc, rbf[nb] = env(x) * sin(f_n x) / x and (optional, for the reverse
+ * sweep) drbf[nb] = d rbf / dx. */
 NN_API int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
-                     int32_t cap_pairs, float* rbf, float* unit, float* dist, void* stream);
-/* reverse of the above: G_p = dE/d disp_p from rbf_bar [P,nb] and unit_bar [P,3]. */
-NN_API int nn_edge_geom_bwd(const float* rbf_bar, const float* unit_bar, const float* unit, const float* dist,
-                     const float* freq, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
-                     float* disp_bar, void* stream);
+                            int32_t cap_pairs, float* rbf, float* drbf, float* unit, float* dist, void* stream);
+/* reverse of the above: G_p = dE/d disp_p from x_bar [P] (= dE/dx) and unit_bar [P,3]. */
+NN_API int nn_edge_geom_bwd(const float* x_bar, const float* unit_bar, const float* unit, const float* dist,
+                            float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs, float* disp_bar,
+                            void* stream);
 /* m_p = (We rbf_p) * mn_i * mn_j, models/newtonnet.py:210-211. */
 NN_API int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const float* mn, const float* Wet,
                         float* msg, void* stream);

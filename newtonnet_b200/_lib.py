@@ -74,8 +74,8 @@ SYMBOLS = {
     'nn_get_gemm_backend': (C.c_int, []),
     'nn_eval_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'nn_eval': (C.c_int, [C.POINTER(EvalArgs), _fp]),
-    'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp]),
-    'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
+    'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
+    'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
     'nn_edge_message_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp]),
     'nn_node_aggregate_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_equiv_update_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int32, _fp]),
@@ -104,6 +104,9 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # dense contractions: tcgen05 3xTF32 tensor-core kernel by default; NN_GEMM_BACKEND=simt selects the
+    # fp32 SIMT kernel (both are CUDA kernels of this library - there is no non-CUDA path)
+    lib.nn_set_gemm_backend(0 if os.environ.get('NN_GEMM_BACKEND', 'tc') == 'simt' else 1)
     _lib = lib
     return lib
 

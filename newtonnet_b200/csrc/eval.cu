@@ -15,8 +15,8 @@ int nn_energy_head_seed_launch(const float* h2pre, const float* w3, const float*
                                float* gh2, cudaStream_t s);
 int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
                               float* e2bar, float* ubar, bool first, cudaStream_t s);
-int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* Wet,
-                               float* mbar_io, float* rbf_bar, cudaStream_t s);
+int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
+                               const float* Wet, float* mbar_io, float* x_bar, cudaStream_t s);
 int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
                                  float* mnbar, float* fbar_new, bool first, cudaStream_t s);
 
@@ -111,13 +111,13 @@ struct LayerBuf {
 struct EvalWs {
     LayerBuf layer[NN_MAX_LAYERS];
     float *a0, *a1;                       // [N,F] ping-pong invariant features
-    float *rbf, *unit, *dist;             // [P,nb], [P,3], [P]
+    float *rbf, *drbf, *unit, *dist;      // [P,nb], [P,nb] (d rbf / dx), [P,3], [P]
     float *h1pre, *h2pre, *e_atom;        // head
     // reverse sweep
     float *abar, *mnbar, *tmpN;           // [N,F]
     float *fbar, *dfb;                    // [N,3,F]
     float *e2bar, *mbar;                  // [P,F]
-    float *rbf_bar, *ubar, *G;            // [P,nb], [P,3], [P,3]
+    float *x_bar, *ubar, *G;              // [P] (dE/dx), [P,3], [P,3]
     float *vir_atom;                      // [N,9]
     size_t total;
 };
@@ -135,12 +135,13 @@ EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
     }
     w.a0 = c.take<float>(NF); w.a1 = c.take<float>(NF);
     w.rbf = c.take<float>((size_t)P * kNB); w.unit = c.take<float>((size_t)P * 3); w.dist = c.take<float>(P);
+    w.drbf = bwd ? c.take<float>((size_t)P * kNB) : nullptr;
     w.h1pre = c.take<float>(NF); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
     if (bwd) {
         w.abar = c.take<float>(NF); w.mnbar = c.take<float>(NF); w.tmpN = c.take<float>(NF);
         w.fbar = c.take<float>(3 * NF); w.dfb = c.take<float>(3 * NF);
         w.e2bar = c.take<float>(PF); w.mbar = c.take<float>(PF);
-        w.rbf_bar = c.take<float>((size_t)P * kNB); w.ubar = c.take<float>((size_t)P * 3); w.G = c.take<float>((size_t)P * 3);
+        w.x_bar = c.take<float>(P); w.ubar = c.take<float>((size_t)P * 3); w.G = c.take<float>((size_t)P * 3);
         w.vir_atom = c.take<float>((size_t)N * 9);
     }
     w.total = c.off;
@@ -199,7 +200,7 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
     const int PRO_ACT = bwd ? NN_PRO_SILU_SAVE : NN_PRO_SILU;
 
     // ---- edge features (R3-R6) and embedding (R1)
-    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.unit, w.dist, s)); }
+    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.drbf, w.unit, w.dist, s)); }
     float* a_cur = w.a0;
     float* a_nxt = w.a1;
     { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_embed_launch(a->z, W.embedding, a_cur, N, nl->status, s)); }
@@ -243,7 +244,7 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
     g.bwd(w.mnbar, W.H1, w.abar, N, NN_PRO_NONE, NN_EPI_BIAS);                                       // abar
     NN_TRY(g.rc);
     cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
-    cudaMemsetAsync(w.rbf_bar, 0, (size_t)P * kNB * sizeof(float), s);
+    cudaMemsetAsync(w.x_bar, 0, (size_t)P * sizeof(float), s);
     cudaMemsetAsync(w.ubar, 0, (size_t)P * 3 * sizeof(float), s);
     float* fbar = w.fbar;
     float* dfb = w.dfb;
@@ -264,7 +265,7 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
             g.bwd(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
         }
         NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, lw.Wet, w.mbar, w.rbf_bar, s)); }
+        { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, w.drbf, lw.Wet, w.mbar, w.x_bar, s)); }
         { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, w.mbar, b.mn, b.e2, dfb, w.mnbar, fbar, first, s)); }
         // abar += ((mnbar @ W2) * silu'(pre)) @ W1
         g.bwd(w.mnbar, lw.W2, w.tmpN, N, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
@@ -272,7 +273,7 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
         NN_TRY(g.rc);
         // fbar of the next (lower) layer was written into `fbar`; dfb is scratch again
     }
-    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.rbf_bar, w.ubar, w.unit, w.dist, W.frequencies, W.cutoff, np_dev, P, w.G, s)); }
+    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
     {
         ProfScope ps(NN_STAGE_FORCE, s);
         NN_TRY(nn_force_virial_reduce(nl, w.G, a->forces, a->want_virial ? a->virial : nullptr,

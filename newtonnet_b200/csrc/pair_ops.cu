@@ -40,7 +40,7 @@ __device__ __forceinline__ float envelope_grad(float x) {
 
 __global__ void k_edge_geom_fwd(const float* __restrict__ disp, const float* __restrict__ freq, float cutoff,
                                 const int* __restrict__ n_dev, int cap, float* __restrict__ rbf,
-                                float* __restrict__ unit, float* __restrict__ dist) {
+                                float* __restrict__ drbf, float* __restrict__ unit, float* __restrict__ dist) {
     const int P = dev_count(n_dev, cap);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         float3 d3 = make_float3(disp[3 * p], disp[3 * p + 1], disp[3 * p + 2]);
@@ -48,37 +48,31 @@ __global__ void k_edge_geom_fwd(const float* __restrict__ disp, const float* __r
         unit[3 * p] = __fdiv_rn(d3.x, d); unit[3 * p + 1] = __fdiv_rn(d3.y, d); unit[3 * p + 2] = __fdiv_rn(d3.z, d);
         dist[p] = d;
         float x = __fdiv_rn(d, cutoff);
-        float s = envelope(x) / x;
-#pragma unroll
-        for (int n = 0; n < kNB; ++n) rbf[(size_t)p * kNB + n] = s * sinf(freq[n] * x);
-    }
-}
-
-// G_p = dE/d disp_p = (xbar / rc) u + (ubar - <ubar,u> u) / d,
-// xbar = sum_n rbfbar_n (env' sb_n + env sb'_n), sb_n = sin(f x)/x, sb'_n = (f x cos(f x) - sin(f x))/x^2.
-__global__ void k_edge_geom_bwd(const float* __restrict__ rbf_bar, const float* __restrict__ unit_bar,
-                                const float* __restrict__ unit, const float* __restrict__ dist,
-                                const float* __restrict__ freq, float cutoff, const int* __restrict__ n_dev,
-                                int cap, float* __restrict__ disp_bar) {
-    const int P = dev_count(n_dev, cap);
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        float d = dist[p];
-        float x = __fdiv_rn(d, cutoff);
-        float env = envelope(x), envp = envelope_grad(x);
-        float invx = 1.0f / x;
-        float xbar = 0.f;
+        float env = envelope(x), envp = envelope_grad(x), invx = 1.0f / x;
 #pragma unroll
         for (int n = 0; n < kNB; ++n) {
             float fx = freq[n] * x, sn, cs;
             sincosf(fx, &sn, &cs);
             float sb = sn * invx;
-            float sbp = (fx * cs - sn) * invx * invx;
-            xbar = fmaf(rbf_bar[(size_t)p * kNB + n], fmaf(envp, sb, env * sbp), xbar);
+            rbf[(size_t)p * kNB + n] = env * sb;
+            // d/dx [env(x) sin(f x)/x] = env' sb + env (f x cos(f x) - sin(f x)) / x^2
+            if (drbf) drbf[(size_t)p * kNB + n] = fmaf(envp, sb, env * (fx * cs - sn) * invx * invx);
         }
+    }
+}
+
+// G_p = dE/d disp_p = (xbar / rc) u + (ubar - <ubar,u> u) / d, with xbar = dE/dx accumulated by the
+// reverse message kernels (xbar_p = sum_layers <y_p, We drbf_p>).
+__global__ void k_edge_geom_bwd(const float* __restrict__ x_bar, const float* __restrict__ unit_bar,
+                                const float* __restrict__ unit, const float* __restrict__ dist, float cutoff,
+                                const int* __restrict__ n_dev, int cap, float* __restrict__ disp_bar) {
+    const int P = dev_count(n_dev, cap);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        float d = dist[p];
         float3 u = make_float3(unit[3 * p], unit[3 * p + 1], unit[3 * p + 2]);
         float3 ub = make_float3(unit_bar[3 * p], unit_bar[3 * p + 1], unit_bar[3 * p + 2]);
         float dot = ub.x * u.x + ub.y * u.y + ub.z * u.z;
-        float a = xbar / cutoff, invd = 1.0f / d;
+        float a = x_bar[p] / cutoff, invd = 1.0f / d;
         disp_bar[3 * p] = fmaf(a, u.x, (ub.x - dot * u.x) * invd);
         disp_bar[3 * p + 1] = fmaf(a, u.y, (ub.y - dot * u.y) * invd);
         disp_bar[3 * p + 2] = fmaf(a, u.z, (ub.z - dot * u.z) * invd);
@@ -101,21 +95,26 @@ __device__ __forceinline__ float4 edge_part(const float* __restrict__ s_wet, con
     return me;
 }
 
+// Pairs are stored grouped by their lower atom i (pair_ptr), so one warp walks the forward pairs of one
+// atom: the i-side rows are loaded once per atom and only the j-side rows are gathered per pair.
 __global__ void __launch_bounds__(kThreads, 3)
-k_edge_message_fwd(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
-                   int cap, const float* __restrict__ rbf, const float* __restrict__ mn,
+k_edge_message_fwd(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
+                   const float* __restrict__ rbf, const float* __restrict__ mn,
                    const float* __restrict__ Wet, float* __restrict__ msg) {
     __shared__ __align__(16) float s_wet[kNB * kF];
     for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
     __syncthreads();
-    const int P = dev_count(n_dev, cap);
     const int lane = threadIdx.x & 31;
-    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
-        int i = pair_i[p], j = pair_j[p];
-        float4 a = ld4(mn + (size_t)i * kF + 4 * lane);
-        float4 b = ld4(mn + (size_t)j * kF + 4 * lane);
-        float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
-        st4(msg + (size_t)p * kF + 4 * lane, f4_mul(me, f4_mul(a, b)));
+    for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
+        const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
+        if (p0 >= p1) continue;
+        const float4 a = ld4(mn + (size_t)i * kF + 4 * lane);
+        for (int p = p0; p < p1; ++p) {
+            const int j = pair_j[p];
+            float4 b = ld4(mn + (size_t)j * kF + 4 * lane);
+            float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
+            st4(msg + (size_t)p * kF + 4 * lane, f4_mul(me, f4_mul(a, b)));
+        }
     }
 }
 
@@ -245,66 +244,84 @@ __global__ void k_energy_head_seed(const float* __restrict__ h2pre, const float*
 // e2bar = sum_c dfb_i[c] * f_in_j[c] + dfb_j[c] * f_in_i[c]
 template <bool FIRST>
 __global__ void __launch_bounds__(kThreads)
-k_pair_bwd_gather(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
-                  int cap, const float* __restrict__ dfb, const float* __restrict__ f_in,
+k_pair_bwd_gather(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
+                  const float* __restrict__ dfb, const float* __restrict__ f_in,
                   const float* __restrict__ unit, float* __restrict__ e1_io, float* __restrict__ e2bar,
                   float* __restrict__ ubar) {
-    const int P = dev_count(n_dev, cap);
     const int lane = threadIdx.x & 31;
-    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
-        const int i = pair_i[p], j = pair_j[p];
+    for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
+        const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
+        if (p0 >= p1) continue;
         const float* di = dfb + (size_t)i * 3 * kF + 4 * lane;
-        const float* dj = dfb + (size_t)j * 3 * kF + 4 * lane;
-        float4 dix = ld4(di), diy = ld4(di + kF), diz = ld4(di + 2 * kF);
-        float4 djx = ld4(dj), djy = ld4(dj + kF), djz = ld4(dj + 2 * kF);
-        float4 wx = f4_sub(dix, djx), wy = f4_sub(diy, djy), wz = f4_sub(diz, djz);
-        const float ux = unit[3 * p], uy = unit[3 * p + 1], uz = unit[3 * p + 2];
-        const size_t po = (size_t)p * kF + 4 * lane;
-        float4 v1 = ld4(e1_io + po);
-        float sx = warp_sum(f4_dot(wx, v1)), sy = warp_sum(f4_dot(wy, v1)), sz = warp_sum(f4_dot(wz, v1));
-        if (lane == 0) { ubar[3 * p] += sx; ubar[3 * p + 1] += sy; ubar[3 * p + 2] += sz; }
-        float4 e1b = make_float4(0.f, 0.f, 0.f, 0.f);
-        e1b = f4_fma(ux, wx, e1b); e1b = f4_fma(uy, wy, e1b); e1b = f4_fma(uz, wz, e1b);
-        st4(e1_io + po, e1b);
+        const float4 dix = ld4(di), diy = ld4(di + kF), diz = ld4(di + 2 * kF);
+        float4 fix = f4_zero(), fiy = f4_zero(), fiz = f4_zero();
         if (!FIRST) {
             const float* fi = f_in + (size_t)i * 3 * kF + 4 * lane;
-            const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
-            float4 acc = f4_mul(dix, ld4(fj));
-            acc = f4_fma(diy, ld4(fj + kF), acc); acc = f4_fma(diz, ld4(fj + 2 * kF), acc);
-            acc = f4_fma(djx, ld4(fi), acc); acc = f4_fma(djy, ld4(fi + kF), acc); acc = f4_fma(djz, ld4(fi + 2 * kF), acc);
-            st4(e2bar + po, acc);
+            fix = ld4(fi); fiy = ld4(fi + kF); fiz = ld4(fi + 2 * kF);
+        }
+        for (int p = p0; p < p1; ++p) {
+            const int j = pair_j[p];
+            const float* dj = dfb + (size_t)j * 3 * kF + 4 * lane;
+            const float4 djx = ld4(dj), djy = ld4(dj + kF), djz = ld4(dj + 2 * kF);
+            const float4 wx = f4_sub(dix, djx), wy = f4_sub(diy, djy), wz = f4_sub(diz, djz);
+            const float ux = unit[3 * p], uy = unit[3 * p + 1], uz = unit[3 * p + 2];
+            const size_t po = (size_t)p * kF + 4 * lane;
+            const float4 v1 = ld4(e1_io + po);
+            float sx = warp_sum(f4_dot(wx, v1)), sy = warp_sum(f4_dot(wy, v1)), sz = warp_sum(f4_dot(wz, v1));
+            if (lane == 0) { ubar[3 * p] += sx; ubar[3 * p + 1] += sy; ubar[3 * p + 2] += sz; }
+            float4 e1b = f4_zero();
+            e1b = f4_fma(ux, wx, e1b); e1b = f4_fma(uy, wy, e1b); e1b = f4_fma(uz, wz, e1b);
+            st4(e1_io + po, e1b);
+            if (!FIRST) {
+                const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
+                float4 acc = f4_mul(dix, ld4(fj));
+                acc = f4_fma(diy, ld4(fj + kF), acc); acc = f4_fma(diz, ld4(fj + 2 * kF), acc);
+                acc = f4_fma(djx, fix, acc); acc = f4_fma(djy, fiy, acc); acc = f4_fma(djz, fiz, acc);
+                st4(e2bar + po, acc);
+            }
         }
     }
 }
 
-// mtot = mbar + abar_i + abar_j;  rbfbar += (mtot * mn_i * mn_j) We;  t = mtot * me  (overwrites mbar)
+// mtot = mbar + abar_i + abar_j;  y = mtot * mn_i * mn_j;  xbar_p += <y, We drbf_p>  (one warp reduction:
+// dE/dx is contracted with We here, instead of keeping a 20-wide rbf gradient per pair);
+// t = mtot * (We rbf_p)  (overwrites mbar)
 __global__ void __launch_bounds__(kThreads, 3)
-k_pair_bwd_message(const int* __restrict__ pair_i, const int* __restrict__ pair_j, const int* __restrict__ n_dev,
-                   int cap, const float* __restrict__ abar, const float* __restrict__ mn,
-                   const float* __restrict__ rbf, const float* __restrict__ Wet, float* __restrict__ mbar_io,
-                   float* __restrict__ rbf_bar) {
+k_pair_bwd_message(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
+                   const float* __restrict__ abar, const float* __restrict__ mn,
+                   const float* __restrict__ rbf, const float* __restrict__ drbf, const float* __restrict__ Wet,
+                   float* __restrict__ mbar_io, float* __restrict__ x_bar) {
     __shared__ __align__(16) float s_wet[kNB * kF];
     for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
     __syncthreads();
-    const int P = dev_count(n_dev, cap);
     const int lane = threadIdx.x & 31;
-    for (int p = blockIdx.x * kWarps + (threadIdx.x >> 5); p < P; p += gridDim.x * kWarps) {
-        const int i = pair_i[p], j = pair_j[p];
-        const size_t po = (size_t)p * kF + 4 * lane;
-        float4 mt = ld4(mbar_io + po);
-        mt = f4_add(mt, f4_add(ld4(abar + (size_t)i * kF + 4 * lane), ld4(abar + (size_t)j * kF + 4 * lane)));
-        float4 prod = f4_mul(ld4(mn + (size_t)i * kF + 4 * lane), ld4(mn + (size_t)j * kF + 4 * lane));
-        float4 y = f4_mul(mt, prod);
-        // rbfbar_n = sum_f y_f We[f,n]: per-lane partials, then a warp reduction per basis function
-        float mine = 0.f;
-#pragma unroll 4
-        for (int n = 0; n < kNB; ++n) {
-            float part = warp_sum(f4_dot(y, ld4(s_wet + n * kF + 4 * lane)));
-            if (lane == n) mine = part;
+    for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
+        const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
+        if (p0 >= p1) continue;
+        const float4 ab_i = ld4(abar + (size_t)i * kF + 4 * lane);
+        const float4 mn_i = ld4(mn + (size_t)i * kF + 4 * lane);
+        for (int p = p0; p < p1; ++p) {
+            const int j = pair_j[p];
+            const size_t po = (size_t)p * kF + 4 * lane;
+            float4 mt = f4_add(ld4(mbar_io + po), f4_add(ab_i, ld4(abar + (size_t)j * kF + 4 * lane)));
+            const float4 y = f4_mul(mt, f4_mul(mn_i, ld4(mn + (size_t)j * kF + 4 * lane)));
+            // me = We rbf_p and dme = We drbf_p share the We loads
+            float4 me = f4_zero(), dme = f4_zero();
+            const float* r = rbf + (size_t)p * kNB;
+            const float* dr = drbf + (size_t)p * kNB;
+#pragma unroll 1
+            for (int q = 0; q < kNB / 4; ++q) {
+                const float4 rv = ld4(r + 4 * q), dv = ld4(dr + 4 * q);
+                float4 w;
+                w = ld4(s_wet + (4 * q + 0) * kF + 4 * lane); me = f4_fma(rv.x, w, me); dme = f4_fma(dv.x, w, dme);
+                w = ld4(s_wet + (4 * q + 1) * kF + 4 * lane); me = f4_fma(rv.y, w, me); dme = f4_fma(dv.y, w, dme);
+                w = ld4(s_wet + (4 * q + 2) * kF + 4 * lane); me = f4_fma(rv.z, w, me); dme = f4_fma(dv.z, w, dme);
+                w = ld4(s_wet + (4 * q + 3) * kF + 4 * lane); me = f4_fma(rv.w, w, me); dme = f4_fma(dv.w, w, dme);
+            }
+            const float xs = warp_sum(f4_dot(y, dme));
+            if (lane == 0) x_bar[p] += xs;
+            st4(mbar_io + po, f4_mul(mt, me));
         }
-        if (lane < kNB) rbf_bar[(size_t)p * kNB + lane] += mine;
-        float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
-        st4(mbar_io + po, f4_mul(mt, me));
     }
 }
 
@@ -459,21 +476,21 @@ int grid_for_rows(long long rows) {
 
 // ============================================================================ host launchers
 extern "C" int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
-                                int32_t cap_pairs, float* rbf, float* unit, float* dist, void* stream) {
+                                int32_t cap_pairs, float* rbf, float* drbf, float* unit, float* dist, void* stream) {
     if (cap_pairs <= 0) return 0;
     int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
-    k_edge_geom_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, unit, dist); NN_LAUNCHED(1);
+    k_edge_geom_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, drbf, unit, dist); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_fwd");
     return 0;
 }
 
-extern "C" int nn_edge_geom_bwd(const float* rbf_bar, const float* unit_bar, const float* unit, const float* dist,
-                                const float* freq, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
-                                float* disp_bar, void* stream) {
+extern "C" int nn_edge_geom_bwd(const float* x_bar, const float* unit_bar, const float* unit, const float* dist,
+                                float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs, float* disp_bar,
+                                void* stream) {
     if (cap_pairs <= 0) return 0;
     int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
-    k_edge_geom_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(rbf_bar, unit_bar, unit, dist, freq, cutoff, n_pairs_dev,
-                                                           cap_pairs, disp_bar); NN_LAUNCHED(1);
+    k_edge_geom_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(x_bar, unit_bar, unit, dist, cutoff, n_pairs_dev, cap_pairs,
+                                                           disp_bar); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_bwd");
     return 0;
 }
@@ -481,8 +498,8 @@ extern "C" int nn_edge_geom_bwd(const float* rbf_bar, const float* unit_bar, con
 extern "C" int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const float* mn, const float* Wet, float* msg,
                                    void* stream) {
     if (nl->cap_pairs <= 0) return 0;
-    k_edge_message_fwd<<<grid_for_rows(nl->cap_pairs), kThreads, 0, (cudaStream_t)stream>>>(
-        nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs, rbf, mn, Wet, msg); NN_LAUNCHED(1);
+    k_edge_message_fwd<<<grid_for_rows(nl->n_atoms), kThreads, 0, (cudaStream_t)stream>>>(
+        nl->pair_ptr, nl->pair_j, nl->n_atoms, nl->cap_pairs, rbf, mn, Wet, msg); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_message_fwd");
     return 0;
 }
@@ -560,23 +577,23 @@ int nn_energy_head_seed_launch(const float* h2pre, const float* w3, const float*
 int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
                               float* e2bar, float* ubar, bool first, cudaStream_t s) {
     if (nl->cap_pairs <= 0) return 0;
-    int grid = grid_for_rows(nl->cap_pairs);
+    int grid = grid_for_rows(nl->n_atoms);
     if (first) {
-        k_pair_bwd_gather<true><<<grid, kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs,
+        k_pair_bwd_gather<true><<<grid, kThreads, 0, s>>>(nl->pair_ptr, nl->pair_j, nl->n_atoms, nl->cap_pairs,
                                                            dfb, f_in, unit, e1_io, e2bar, ubar); NN_LAUNCHED(1);
     }
     else {
-        k_pair_bwd_gather<false><<<grid, kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS, nl->cap_pairs,
+        k_pair_bwd_gather<false><<<grid, kThreads, 0, s>>>(nl->pair_ptr, nl->pair_j, nl->n_atoms, nl->cap_pairs,
                                                             dfb, f_in, unit, e1_io, e2bar, ubar); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("pair_bwd_gather");
     return 0;
 }
-int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* Wet,
-                               float* mbar_io, float* rbf_bar, cudaStream_t s) {
+int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
+                               const float* Wet, float* mbar_io, float* x_bar, cudaStream_t s) {
     if (nl->cap_pairs <= 0) return 0;
-    k_pair_bwd_message<<<grid_for_rows(nl->cap_pairs), kThreads, 0, s>>>(nl->pair_i, nl->pair_j, nl->status + NN_ST_N_PAIRS,
-                                                                          nl->cap_pairs, abar, mn, rbf, Wet, mbar_io, rbf_bar); NN_LAUNCHED(1);
+    k_pair_bwd_message<<<grid_for_rows(nl->n_atoms), kThreads, 0, s>>>(nl->pair_ptr, nl->pair_j, nl->n_atoms, nl->cap_pairs,
+                                                                        abar, mn, rbf, drbf, Wet, mbar_io, x_bar); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("pair_bwd_message");
     return 0;
 }

@@ -90,6 +90,6 @@ class EdgeEmbedding(nn.Module):
         freq = self.embedding.frequencies.detach().to(device=dev, dtype=torch.float32).contiguous()
         if E:
             L.check(L.load().nn_edge_geom_fwd(d32.data_ptr(), freq.data_ptr(), float(self.norm.r), None, E,
-                                             rbf.data_ptr(), unit.data_ptr(), dist.data_ptr(), _stream()),
+                                             rbf.data_ptr(), None, unit.data_ptr(), dist.data_ptr(), _stream()),
                     'nn_edge_geom_fwd')
         return rbf.to(pos.dtype), unit.to(pos.dtype), edge_index

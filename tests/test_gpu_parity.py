@@ -34,7 +34,7 @@ def backend(request):
             pytest.skip('tcgen05 backend not built')
     lib.nn_set_gemm_backend(request.param)
     yield request.param
-    lib.nn_set_gemm_backend(0)
+    lib.nn_set_gemm_backend(1)
 
 
 def _tc_available(lib, probe):
@@ -47,7 +47,6 @@ def _tc_available(lib, probe):
     lib.nn_set_gemm_backend(1)
     rc = lib.nn_gemm128(C.byref(a), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    lib.nn_set_gemm_backend(0)
     return rc == 0
 
 
