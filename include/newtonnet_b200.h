@@ -113,6 +113,8 @@ typedef struct {
     int32_t cap_edges;              /* capacity of col / edge_pair */
     int32_t cap_pairs;              /* capacity of pair_* (>= cap_edges / 2) */
     int32_t cap_cells;              /* capacity of the cell arrays (>= 2 * n_atoms + n_systems) */
+    int32_t n_owned;                /* > 0: pairs between two atoms with index >= n_owned (ghost-ghost) are
+                                       dropped (domain decomposition); 0 = keep all */
     const float* pos;               /* [N,3] */
     const float* cell;              /* [B,3,3] rows = lattice vectors; all zero = not periodic */
     const int64_t* batch;           /* [N] system id of each atom, non-decreasing */
@@ -185,6 +187,10 @@ typedef struct {
     const int64_t* z;               /* [N] atomic numbers */
     int32_t want_forces;            /* 0: energy only (no reverse sweep) */
     int32_t want_virial;
+    int32_t n_owned;                /* domain decomposition: atoms [0, n_owned) are owned, [n_owned, N) are
+                                       ghosts whose feature rows the caller refreshes between phases;
+                                       0 = all atoms owned (single GPU) */
+    int32_t pad_;
     /* outputs */
     float* energy;                  /* [B] */
     float* forces;                  /* [N,3] */
@@ -197,6 +203,21 @@ typedef struct {
 NN_API size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, int32_t cap_pairs, int32_t n_layers,
                                int32_t want_forces);
 NN_API int nn_eval(const nn_eval_args* a, void* stream);
+/* The same evaluation split into phases, for spatial domain decomposition: node-level work covers the
+ * owned atoms, pair-level work every local pair (owned-owned and owned-ghost); after the phases marked
+ * [x] the caller copies the named buffers' ghost rows from their owner ranks (halo exchange).
+ *   BEGIN, then per layer l: FWD_NODE(l) [mn(l), and f_out(l-1) if l>0], FWD_PAIR(l); HEAD;
+ *   BWD_SEED, then per layer l = L-1..0: BWD_NODE(l) [dfb, abar], BWD_PAIR(l); FINISH.
+ * energy / virial / stress then hold this rank's partial sums, forces the owned rows. */
+enum { NN_PH_BEGIN = 0, NN_PH_FWD_NODE = 1, NN_PH_FWD_PAIR = 2, NN_PH_HEAD = 3, NN_PH_BWD_SEED = 4,
+       NN_PH_BWD_NODE = 5, NN_PH_BWD_PAIR = 6, NN_PH_FINISH = 7 };
+enum { NN_BUF_MN = 0, NN_BUF_F_OUT = 1, NN_BUF_DFB = 2, NN_BUF_ABAR = 3 };
+NN_API int nn_eval_phase(const nn_eval_args* a, int32_t phase, int32_t layer, void* stream);
+/* device pointer of an exchanged buffer inside the workspace: MN [N,F], F_OUT [N,3,F] (per layer),
+ * DFB [N,3,F], ABAR [N,F]. */
+NN_API float* nn_eval_buffer(const nn_eval_args* a, int32_t which, int32_t layer);
+/* out[k, :] = src[idx[k], :] for k < n (width floats per row): packs the rows a rank sends to a peer. */
+NN_API int nn_halo_pack(const float* src, const int32_t* idx, int32_t n, int32_t width, float* out, void* stream);
 
 /* ------------------------------------------------------------------ staged operators (also used by
  * nn_eval; exported for per-kernel parity tests and for the differentiable training path) */

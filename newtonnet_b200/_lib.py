@@ -17,6 +17,8 @@ NN_B_IMAGE_FLOATS = 2 * 128 * 128
 ST_EDGE_OVERFLOW, ST_ROW_OVERFLOW, ST_BATCH_UNSORTED, ST_SINGULAR_CELL, ST_N_EDGES, ST_N_PAIRS, ST_N_CELLS = range(7)
 STAGES = ['nbr', 'geom', 'node_gemm', 'pair_gemm', 'message', 'aggregate', 'head', 'bwd_gather', 'bwd_message',
           'bwd_aggregate', 'force', 'other']
+PH_BEGIN, PH_FWD_NODE, PH_FWD_PAIR, PH_HEAD, PH_BWD_SEED, PH_BWD_NODE, PH_BWD_PAIR, PH_FINISH = range(8)
+BUF_MN, BUF_F_OUT, BUF_DFB, BUF_ABAR = range(4)
 PRO_NONE, PRO_SILU, PRO_ROWSCALE3, PRO_SILU_SAVE = 0, 1, 2, 3
 EPI_BIAS, EPI_DSILU, EPI_ADD, EPI_EQUIV_BWD, EPI_MUL = 0, 1, 2, 3, 4
 
@@ -40,7 +42,7 @@ class Weights(C.Structure):
 
 class Nbr(C.Structure):
     _fields_ = [('n_atoms', C.c_int32), ('n_systems', C.c_int32), ('cap_edges', C.c_int32),
-                ('cap_pairs', C.c_int32), ('cap_cells', C.c_int32)] + [(n, _fp) for n in (
+                ('cap_pairs', C.c_int32), ('cap_cells', C.c_int32), ('n_owned', C.c_int32)] + [(n, _fp) for n in (
                     'pos', 'cell', 'batch', 'sys_ptr', 'row_ptr', 'col', 'edge_pair', 'pair_ptr', 'pair_i',
                     'pair_j', 'pair_disp', 'status', 'workspace')] + [('workspace_bytes', C.c_size_t)]
 
@@ -53,7 +55,7 @@ class GemmArgs(C.Structure):
 
 class EvalArgs(C.Structure):
     _fields_ = [('nbr', C.POINTER(Nbr)), ('w', C.POINTER(Weights)), ('z', _fp), ('want_forces', C.c_int32),
-                ('want_virial', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
+                ('want_virial', C.c_int32), ('n_owned', C.c_int32), ('pad_', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
                 ('atom_node', _fp), ('force_node', _fp), ('workspace', _fp), ('workspace_bytes', C.c_size_t)]
 
 
@@ -74,6 +76,9 @@ SYMBOLS = {
     'nn_get_gemm_backend': (C.c_int, []),
     'nn_eval_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'nn_eval': (C.c_int, [C.POINTER(EvalArgs), _fp]),
+    'nn_eval_phase': (C.c_int, [C.POINTER(EvalArgs), C.c_int32, C.c_int32, _fp]),
+    'nn_eval_buffer': (C.c_void_p, [C.POINTER(EvalArgs), C.c_int32, C.c_int32]),
+    'nn_halo_pack': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
     'nn_edge_message_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp]),

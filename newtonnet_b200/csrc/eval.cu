@@ -17,8 +17,8 @@ int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f
                               float* e2bar, float* ubar, bool first, cudaStream_t s);
 int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
                                const float* Wet, float* mbar_io, float* x_bar, cudaStream_t s);
-int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
-                                 float* mnbar, float* fbar_new, bool first, cudaStream_t s);
+int nn_node_aggregate_bwd_launch(const nn_nbr* nl, int n_rows, const float* t, const float* mn, const float* e2,
+                                 const float* dfb, float* mnbar, float* fbar_new, bool first, cudaStream_t s);
 
 // ---------------------------------------------------------------------------- error / backend state
 static thread_local char g_err[512] = "";
@@ -182,81 +182,109 @@ extern "C" size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, in
 
 #define NN_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
-extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
+int nn_node_aggregate_fwd_rows(const nn_nbr* nl, int n_rows, const float* msg, const float* e1, const float* e2,
+                               const float* unit, const float* a_in, const float* f_in, float* a_out, float* f_out,
+                               bool first, cudaStream_t s);
+int nn_energy_head_fwd_rows(const float* h2pre, const float* w3, const float* b3, const float* scale, const float* shift,
+                            const int64_t* z, const int32_t* sys_ptr, int n_rows, int n_systems, float* e_atom,
+                            float* energy, cudaStream_t s);
+int nn_force_virial_rows(const nn_nbr* nl, int n_rows, const float* disp_bar, float* forces, float* virial, float* stress,
+                         void* workspace, cudaStream_t s);
+
+namespace {
+
+struct EvalCtx {
+    const nn_eval_args* a; const nn_nbr* nl; const nn_weights* W;
+    int N, No, B, P, L; bool bwd; cudaStream_t s; EvalWs w; const int* np_dev; int PRO_ACT;
+};
+
+int make_ctx(const nn_eval_args* a, void* stream, EvalCtx& c) {
     NN_REQUIRE(a && a->nbr && a->w && a->z && a->energy, "null pointer");
-    const nn_nbr* nl = a->nbr;
-    const nn_weights& W = *a->w;
-    const int N = nl->n_atoms, B = nl->n_systems, P = nl->cap_pairs, L = W.n_layers;
-    NN_REQUIRE(L >= 1 && L <= NN_MAX_LAYERS, "n_layers out of range");
-    const bool bwd = a->want_forces != 0 || a->want_virial != 0;
-    NN_REQUIRE(!bwd || a->forces, "forces buffer required");
+    c.a = a; c.nl = a->nbr; c.W = a->w;
+    c.N = c.nl->n_atoms; c.B = c.nl->n_systems; c.P = c.nl->cap_pairs; c.L = c.W->n_layers;
+    c.No = a->n_owned > 0 ? a->n_owned : c.N;
+    NN_REQUIRE(c.No <= c.N, "n_owned > n_atoms");
+    NN_REQUIRE(c.L >= 1 && c.L <= NN_MAX_LAYERS, "n_layers out of range");
+    c.bwd = a->want_forces != 0 || a->want_virial != 0;
+    NN_REQUIRE(!c.bwd || a->forces, "forces buffer required");
     NN_REQUIRE(!a->want_virial || a->virial, "virial buffer required");
-    NN_REQUIRE(a->workspace_bytes >= nn_eval_workspace_bytes(N, B, P, L, bwd), "workspace too small");
-    cudaStream_t s = (cudaStream_t)stream;
-    EvalWs w = carve_eval(a->workspace, a->workspace_bytes, N, P, L, bwd);
-    const int* np_dev = nl->status + NN_ST_N_PAIRS;
-    Gemm g{s};
+    NN_REQUIRE(a->workspace_bytes >= nn_eval_workspace_bytes(c.N, c.B, c.P, c.L, c.bwd), "workspace too small");
+    c.s = (cudaStream_t)stream;
+    c.w = carve_eval(a->workspace, a->workspace_bytes, c.N, c.P, c.L, c.bwd);
+    c.np_dev = c.nl->status + NN_ST_N_PAIRS;
     // with a reverse sweep the activation GEMMs leave silu'(pre) behind in place of pre
-    const int PRO_ACT = bwd ? NN_PRO_SILU_SAVE : NN_PRO_SILU;
+    c.PRO_ACT = c.bwd ? NN_PRO_SILU_SAVE : NN_PRO_SILU;
+    return 0;
+}
 
-    // ---- edge features (R3-R6) and embedding (R1)
-    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.drbf, w.unit, w.dist, s)); }
-    float* a_cur = w.a0;
-    float* a_nxt = w.a1;
-    { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_embed_launch(a->z, W.embedding, a_cur, N, nl->status, s)); }
-
-    // ---- interaction layers (R7)
-    for (int l = 0; l < L; ++l) {
-        const nn_layer_weights& lw = W.layer[l];
-        LayerBuf& b = w.layer[l];
+// One phase of the evaluation.  Node-level work (GEMMs, aggregations, head) runs on the first `No` (owned)
+// atoms, pair-level work on every local pair; between phases a domain-decomposed caller refreshes the
+// ghost rows [No, N) of the buffer named in the comment (single-GPU: No == N, nothing to exchange).
+int run_phase(EvalCtx& c, int phase, int l) {
+    const nn_weights& W = *c.W; EvalWs& w = c.w; const nn_nbr* nl = c.nl; cudaStream_t s = c.s;
+    const int N = c.N, No = c.No, P = c.P, L = c.L; const int* np_dev = c.np_dev;
+    Gemm g{s};
+    float* a_cur = w.a0; float* a_nxt = w.a1;
+    switch (phase) {
+    case NN_PH_BEGIN: {      // edge features (R3-R6) and embedding (R1)
+        { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_fwd(nl->pair_disp, W.frequencies, W.cutoff, np_dev, P, w.rbf, w.drbf, w.unit, w.dist, s)); }
+        { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_embed_launch(c.a->z, W.embedding, a_cur, No, nl->status, s)); }
+        return 0;
+    }
+    case NN_PH_FWD_NODE: {   // -> mn(l) of owned atoms            [then ghosts of: mn(l), f_out(l-1)]
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
+        g.fwd(a_cur, lw.W1, b.pre, No, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
+        g.fwd(b.pre, lw.W2, b.mn, No, c.PRO_ACT, NN_EPI_BIAS, lw.b2);
+        return g.rc;
+    }
+    case NN_PH_FWD_PAIR: {   // message, edge MLPs, aggregation, equivariant update (R7)
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
-        g.fwd(a_cur, lw.W1, b.pre, N, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
-        g.fwd(b.pre, lw.W2, b.mn, N, PRO_ACT, NN_EPI_BIAS, lw.b2);
-        NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_MESSAGE, s); NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s)); }
         g.fwd(b.msg, lw.U1, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-        g.fwd(b.q1, lw.U2, b.e1, P, PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.fwd(b.q1, lw.U2, b.e1, P, c.PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
             g.fwd(b.msg, lw.V1, b.q2, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-            g.fwd(b.q2, lw.V2, b.e2, P, PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+            g.fwd(b.q2, lw.V2, b.e2, P, c.PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         }
         NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd(nl, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
-        g.fwd(b.f_out, lw.Wu, b.g, 3 * N, NN_PRO_NONE, NN_EPI_BIAS);
+        { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd_rows(nl, No, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
+        g.fwd(b.f_out, lw.Wu, b.g, 3 * No, NN_PRO_NONE, NN_EPI_BIAS);
         NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, N, s)); }
+        { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, No, s)); }
+        return 0;
     }
-
-    // ---- energy head (R8, R9)
-    g.fwd(a_cur, W.H1, w.h1pre, N, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
-    g.fwd(w.h1pre, W.H2, w.h2pre, N, PRO_ACT, NN_EPI_BIAS, W.hb2);
-    NN_TRY(g.rc);
-    { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd(w.h2pre, W.w3, W.hb3, W.scale, W.shift, a->z, nl->sys_ptr, N, B, w.e_atom, a->energy, s)); }
-    if (a->atom_node) cudaMemcpyAsync(a->atom_node, a_cur, (size_t)N * kF * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    if (a->force_node) cudaMemcpyAsync(a->force_node, w.layer[L - 1].f_out, (size_t)N * 3 * kF * sizeof(float),
-                                       cudaMemcpyDeviceToDevice, s);
-    if (!bwd) { NN_CHECK_LAUNCH("nn_eval(forward)"); return 0; }
-
-    // ---- reverse sweep (R10 / row B)
-    { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_seed_launch(w.h2pre, W.w3, W.scale, a->z, N, w.tmpN, s)); }   // gh2
-    g.bwd(w.tmpN, W.H2, w.mnbar, N, NN_PRO_NONE, NN_EPI_MUL, nullptr, w.h1pre);                    // gh1
-    g.bwd(w.mnbar, W.H1, w.abar, N, NN_PRO_NONE, NN_EPI_BIAS);                                       // abar
-    NN_TRY(g.rc);
-    cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
-    cudaMemsetAsync(w.x_bar, 0, (size_t)P * sizeof(float), s);
-    cudaMemsetAsync(w.ubar, 0, (size_t)P * 3 * sizeof(float), s);
-    float* fbar = w.fbar;
-    float* dfb = w.dfb;
-    for (int l = L - 1; l >= 0; --l) {
-        const nn_layer_weights& lw = W.layer[l];
-        LayerBuf& b = w.layer[l];
+    case NN_PH_HEAD: {       // energy head (R8, R9): partial energies over owned atoms
+        g.fwd(a_cur, W.H1, w.h1pre, No, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
+        g.fwd(w.h1pre, W.H2, w.h2pre, No, c.PRO_ACT, NN_EPI_BIAS, W.hb2);
+        NN_TRY(g.rc);
+        { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd_rows(w.h2pre, W.w3, W.hb3, W.scale, W.shift, c.a->z, nl->sys_ptr, No, c.B, w.e_atom, c.a->energy, s)); }
+        if (c.a->atom_node) cudaMemcpyAsync(c.a->atom_node, a_cur, (size_t)No * kF * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (c.a->force_node) cudaMemcpyAsync(c.a->force_node, w.layer[L - 1].f_out, (size_t)No * 3 * kF * sizeof(float),
+                                             cudaMemcpyDeviceToDevice, s);
+        return 0;
+    }
+    case NN_PH_BWD_SEED: {   // reverse sweep (R10 / row B): dE/da of owned atoms
+        { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_seed_launch(w.h2pre, W.w3, W.scale, c.a->z, No, w.tmpN, s)); }
+        g.bwd(w.tmpN, W.H2, w.mnbar, No, NN_PRO_NONE, NN_EPI_MUL, nullptr, w.h1pre);
+        g.bwd(w.mnbar, W.H1, w.abar, No, NN_PRO_NONE, NN_EPI_BIAS);
+        NN_TRY(g.rc);
+        cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
+        cudaMemsetAsync(w.x_bar, 0, (size_t)P * sizeof(float), s);
+        cudaMemsetAsync(w.ubar, 0, (size_t)P * 3 * sizeof(float), s);
+        return 0;
+    }
+    case NN_PH_BWD_NODE: {   // dfb = fbar + abar*g + (abar*f_out) @ Wu  (owned)   [then ghosts of: dfb, abar]
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
+        g.bwd(b.f_out, lw.Wu, w.dfb, 3 * No, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, w.fbar, w.abar, b.g);
+        return g.rc;
+    }
+    case NN_PH_BWD_PAIR: {
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
-        // dfb = fbar + abar*g + (abar*f_out) @ Wu
-        g.bwd(b.f_out, lw.Wu, dfb, 3 * N, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, fbar, w.abar, b.g);
-        NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_BWD_GATHER, s); NN_TRY(nn_pair_bwd_gather_launch(nl, dfb, f_in, w.unit, b.e1, w.e2bar, w.ubar, first, s)); }
+        { ProfScope ps(NN_STAGE_BWD_GATHER, s); NN_TRY(nn_pair_bwd_gather_launch(nl, w.dfb, f_in, w.unit, b.e1, w.e2bar, w.ubar, first, s)); }
         // mbar = ((e1bar @ U2) * silu'(q1)) @ U1 + ((e2bar @ V2) * silu'(q2)) @ V1
         g.bwd(b.e1, lw.U2, b.e1, P, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.q1, nullptr, nullptr, np_dev);
         g.bwd(b.e1, lw.U1, w.mbar, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
@@ -266,18 +294,64 @@ extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, w.drbf, lw.Wet, w.mbar, w.x_bar, s)); }
-        { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, w.mbar, b.mn, b.e2, dfb, w.mnbar, fbar, first, s)); }
+        { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, No, w.mbar, b.mn, b.e2, w.dfb, w.mnbar, w.fbar, first, s)); }
         // abar += ((mnbar @ W2) * silu'(pre)) @ W1
-        g.bwd(w.mnbar, lw.W2, w.tmpN, N, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
-        g.bwd(w.tmpN, lw.W1, w.abar, N, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
-        NN_TRY(g.rc);
-        // fbar of the next (lower) layer was written into `fbar`; dfb is scratch again
+        g.bwd(w.mnbar, lw.W2, w.tmpN, No, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
+        g.bwd(w.tmpN, lw.W1, w.abar, No, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
+        return g.rc;
     }
-    { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
-    {
+    case NN_PH_FINISH: {     // dE/d disp per pair, forces of owned atoms, partial virial
+        { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
         ProfScope ps(NN_STAGE_FORCE, s);
-        NN_TRY(nn_force_virial_reduce(nl, w.G, a->forces, a->want_virial ? a->virial : nullptr,
-                                      a->want_virial ? a->stress : nullptr, w.vir_atom, s));
+        NN_TRY(nn_force_virial_rows(nl, No, w.G, c.a->forces, c.a->want_virial ? c.a->virial : nullptr,
+                                    c.a->want_virial ? c.a->stress : nullptr, w.vir_atom, s));
+        return 0;
+    }
+    }
+    nn_set_error("nn_eval_phase: unknown phase %d", phase);
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int nn_eval_phase(const nn_eval_args* a, int32_t phase, int32_t layer, void* stream) {
+    EvalCtx c;
+    NN_TRY(make_ctx(a, stream, c));
+    NN_REQUIRE(layer >= 0 && layer < c.L, "layer out of range");
+    NN_REQUIRE(c.bwd || phase < NN_PH_BWD_SEED, "reverse-sweep phase without want_forces");
+    NN_TRY(run_phase(c, phase, layer));
+    NN_CHECK_LAUNCH("nn_eval_phase");
+    return 0;
+}
+
+extern "C" float* nn_eval_buffer(const nn_eval_args* a, int32_t which, int32_t layer) {
+    EvalCtx c;
+    if (make_ctx(a, nullptr, c) || layer < 0 || layer >= c.L) return nullptr;
+    switch (which) {
+    case NN_BUF_MN: return c.w.layer[layer].mn;
+    case NN_BUF_F_OUT: return c.w.layer[layer].f_out;
+    case NN_BUF_DFB: return c.w.dfb;
+    case NN_BUF_ABAR: return c.w.abar;
+    }
+    return nullptr;
+}
+
+extern "C" int nn_eval(const nn_eval_args* a, void* stream) {
+    EvalCtx c;
+    NN_TRY(make_ctx(a, stream, c));
+    NN_TRY(run_phase(c, NN_PH_BEGIN, 0));
+    for (int l = 0; l < c.L; ++l) {
+        NN_TRY(run_phase(c, NN_PH_FWD_NODE, l));
+        NN_TRY(run_phase(c, NN_PH_FWD_PAIR, l));
+    }
+    NN_TRY(run_phase(c, NN_PH_HEAD, 0));
+    if (c.bwd) {
+        NN_TRY(run_phase(c, NN_PH_BWD_SEED, 0));
+        for (int l = c.L - 1; l >= 0; --l) {
+            NN_TRY(run_phase(c, NN_PH_BWD_NODE, l));
+            NN_TRY(run_phase(c, NN_PH_BWD_PAIR, l));
+        }
+        NN_TRY(run_phase(c, NN_PH_FINISH, 0));
     }
     NN_CHECK_LAUNCH("nn_eval");
     return 0;

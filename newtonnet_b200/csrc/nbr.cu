@@ -230,7 +230,7 @@ template <bool FILL>
 __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __restrict__ pos,
                                                 const SysMeta& m, const int* __restrict__ cell_start,
                                                 const int* __restrict__ sorted_atoms, float cutoff,
-                                                int* __restrict__ row_buf) {
+                                                int n_owned, int* __restrict__ row_buf) {
     const float3 pi = make_float3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
     int c[3];
     cell_coords(m, pi.x, pi.y, pi.z, c);
@@ -255,7 +255,7 @@ __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __
                     int j = -1;
                     if (s < s1) {
                         j = sorted_atoms[s];
-                        if (j != i) {
+                        if (j != i && (i < n_owned || j < n_owned)) {   // ghost-ghost pairs belong to other ranks
                             float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]),
                                                    __fsub_rn(pi.z, pos[3 * j + 2]));
                             d = nn_min_image(d, m, nullptr);
@@ -278,12 +278,13 @@ __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_nbr_count(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
             const SysMeta* __restrict__ meta, const int* __restrict__ cell_start,
-            const int* __restrict__ sorted_atoms, float cutoff, int* __restrict__ deg, int* __restrict__ status) {
+            const int* __restrict__ sorted_atoms, float cutoff, int n_owned, int* __restrict__ deg,
+            int* __restrict__ status) {
     int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (i >= N) return;
     SysMeta m = meta[batch[i]];
-    int found = visit_neighbours<false>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, nullptr);
+    int found = visit_neighbours<false>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, n_owned, nullptr);
     if (lane == 0) {
         if (found > NN_MAX_DEGREE) { atomicMax(&status[NN_ST_ROW_OVERFLOW], found); found = NN_MAX_DEGREE; }
         deg[i] = found;
@@ -301,7 +302,7 @@ __global__ void k_finish_count(const int* __restrict__ row_ptr, int N, int cap_e
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_nbr_fill(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N,
            const SysMeta* __restrict__ meta, const int* __restrict__ cell_start,
-           const int* __restrict__ sorted_atoms, float cutoff, const int* __restrict__ row_ptr,
+           const int* __restrict__ sorted_atoms, float cutoff, int n_owned, const int* __restrict__ row_ptr,
            int cap_edges, int* __restrict__ col, int* __restrict__ fwd_cnt, const int* __restrict__ status) {
     __shared__ int s_rows[kWarpsPerBlock][NN_MAX_DEGREE];
     if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
@@ -310,7 +311,7 @@ k_nbr_fill(const float* __restrict__ pos, const int64_t* __restrict__ batch, int
     if (i >= N) return;
     SysMeta m = meta[batch[i]];
     int* buf = s_rows[w];
-    int found = visit_neighbours<true>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, buf);
+    int found = visit_neighbours<true>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, n_owned, buf);
     if (found > NN_MAX_DEGREE) found = NN_MAX_DEGREE;
     __syncwarp();
     const int base = row_ptr[i];
@@ -418,7 +419,8 @@ extern "C" int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream) {
         cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.cell_count, w.cell_start, cap_cells + 1, s); NN_LAUNCHED(2);
         k_bin_fill<<<nn_ceil_div(N, 256), 256, 0, s>>>(N, w.atom_cell, w.cell_start, w.cell_fill, w.sorted_atoms); NN_LAUNCHED(1);
         k_nbr_count<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, w.deg, nl->status); NN_LAUNCHED(1);
+            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->n_owned > 0 ? nl->n_owned : N, w.deg,
+            nl->status); NN_LAUNCHED(1);
     }
     size_t tb = w.scan_tmp_bytes;
     cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.deg, nl->row_ptr, N + 1, s); NN_LAUNCHED(2);
@@ -436,7 +438,8 @@ extern "C" int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream) {
     NbrWs w = carve(nl->workspace, nl->workspace_bytes, N, B);
     if (N > 0) {
         k_nbr_fill<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->row_ptr, nl->cap_edges,
+            nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->n_owned > 0 ? nl->n_owned : N,
+            nl->row_ptr, nl->cap_edges,
             nl->col, w.fwd_cnt, nl->status); NN_LAUNCHED(1);
     }
     size_t tb = w.scan_tmp_bytes;

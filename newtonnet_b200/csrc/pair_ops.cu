@@ -210,12 +210,13 @@ k_energy_atom(const float* __restrict__ h2pre, const float* __restrict__ w3, con
 }
 
 // fixed-order fp64 sum per system (the reference sums sequentially in fp32; |shift| makes E large)
-__global__ void k_energy_sum(const float* __restrict__ e_atom, const int* __restrict__ sys_ptr,
+__global__ void k_energy_sum(const float* __restrict__ e_atom, const int* __restrict__ sys_ptr, int n_rows,
                              float* __restrict__ energy) {
     __shared__ double s[kThreads];
     int b = blockIdx.x;
     double acc = 0.0;
-    for (int i = sys_ptr[b] + threadIdx.x; i < sys_ptr[b + 1]; i += kThreads) acc += (double)e_atom[i];
+    const int last = min(sys_ptr[b + 1], n_rows);
+    for (int i = sys_ptr[b] + threadIdx.x; i < last; i += kThreads) acc += (double)e_atom[i];
     s[threadIdx.x] = acc;
     __syncthreads();
     for (int o = kThreads / 2; o > 0; o >>= 1) {
@@ -366,15 +367,18 @@ k_node_aggregate_bwd(const int* __restrict__ status, const int* __restrict__ row
 //   M[a,b] = sum_p dpos_a G_b - (cell^T G)_a n_b,  dE/dD = (M + M^T)/2, virial = -dE/dD.
 // With dpos = disp + cell n:  sym(M) = sym(disp (x) G) + sym(X),  X[a,b] = (cell n)_a G_b - (cell^T G)_a n_b.
 // sym(X) vanishes for cubic cells, is (L_a - L_b)(n_a G_b - G_a n_b)/2 for diagonal cells, and is the
-// reference's (unphysical but reproducible) extra term otherwise.  Each atom accumulates its forward
-// pairs; systems are summed in fp64 in fixed order.
+// reference's (unphysical but reproducible) extra term otherwise.  Every pair term is invariant under
+// swapping the pair's orientation, so each atom takes HALF of every incident edge: under domain
+// decomposition the owner of the other endpoint adds the other half.  Systems are summed in fp64 in
+// fixed order.
 __global__ void __launch_bounds__(128)
 k_force_virial_atom(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                    const int* __restrict__ edge_pair, int N, const float* __restrict__ G, const float* __restrict__ pair_disp,
-                    const float* __restrict__ pos, const int64_t* __restrict__ batch,
-                    const SysMeta* __restrict__ meta, float* __restrict__ forces, float* __restrict__ vir_atom) {
+                    const int* __restrict__ edge_pair, int n_rows, const float* __restrict__ G,
+                    const float* __restrict__ pair_disp, const float* __restrict__ pos,
+                    const int64_t* __restrict__ batch, const SysMeta* __restrict__ meta,
+                    float* __restrict__ forces, float* __restrict__ vir_atom) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;
+    if (i >= n_rows || status[NN_ST_EDGE_OVERFLOW] != 0) return;
     const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
     float fx = 0.f, fy = 0.f, fz = 0.f;
     float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -389,17 +393,17 @@ k_force_virial_atom(const int* __restrict__ status, const int* __restrict__ row_
         quirk = sm.mode == 2 || (sm.mode == 1 && !(sm.L[0] == sm.L[1] && sm.L[1] == sm.L[2]));
     }
     for (int e = r0; e < r1; ++e) {
-        int ep = edge_pair[e];
-        int p = ep & 0x7fffffff;
-        float gg[3] = {G[3 * p], G[3 * p + 1], G[3 * p + 2]};
-        if (ep < 0) { fx += gg[0]; fy += gg[1]; fz += gg[2]; continue; }
+        const int ep = edge_pair[e];
+        const int p = ep & 0x7fffffff;
+        const float sgn = ep < 0 ? -1.0f : 1.0f;
+        const float gg[3] = {sgn * G[3 * p], sgn * G[3 * p + 1], sgn * G[3 * p + 2]};     // dE/d disp of THIS edge
         fx -= gg[0]; fy -= gg[1]; fz -= gg[2];
         if (!want_vir) continue;
-        float dp[3] = {pair_disp[3 * p], pair_disp[3 * p + 1], pair_disp[3 * p + 2]};
+        const float dp[3] = {sgn * pair_disp[3 * p], sgn * pair_disp[3 * p + 1], sgn * pair_disp[3 * p + 2]};
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.5f * (dp[a] * gg[b] + dp[b] * gg[a]);
+            for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.25f * (dp[a] * gg[b] + dp[b] * gg[a]);
         if (quirk) {
             int j = col[e];
             float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]), __fsub_rn(pi.z, pos[3 * j + 2]));
@@ -427,7 +431,7 @@ k_force_virial_atom(const int* __restrict__ status, const int* __restrict__ row_
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.5f * (X[3 * a + b] + X[3 * b + a]);
+                for (int b = 0; b < 3; ++b) m[3 * a + b] += 0.25f * (X[3 * a + b] + X[3 * b + a]);
         }
     }
     forces[3 * i] = fx; forces[3 * i + 1] = fy; forces[3 * i + 2] = fz;
@@ -437,12 +441,13 @@ k_force_virial_atom(const int* __restrict__ status, const int* __restrict__ row_
     }
 }
 
-__global__ void k_virial_sum(const float* __restrict__ vir_atom, const int* __restrict__ sys_ptr,
+__global__ void k_virial_sum(const float* __restrict__ vir_atom, const int* __restrict__ sys_ptr, int n_rows,
                              const float* __restrict__ cell, float* __restrict__ virial, float* __restrict__ stress) {
     __shared__ double s[kThreads][9];
     int b = blockIdx.x;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = sys_ptr[b] + threadIdx.x; i < sys_ptr[b + 1]; i += kThreads)
+    const int last = min(sys_ptr[b + 1], n_rows);
+    for (int i = sys_ptr[b] + threadIdx.x; i < last; i += kThreads)
         for (int k = 0; k < 9; ++k) acc[k] += (double)vir_atom[(size_t)i * 9 + k];
     for (int k = 0; k < 9; ++k) s[threadIdx.x][k] = acc[k];
     __syncthreads();
@@ -463,6 +468,16 @@ __global__ void k_virial_sum(const float* __restrict__ vir_atom, const int* __re
                          (double)h[2] * ((double)h[3] * h[7] - (double)h[4] * h[6]);
             stress[9 * b + threadIdx.x] = (float)(gd / det);
         }
+    }
+}
+
+// out[k,:] = src[idx[k],:]  (rows of `width` floats, width % 4 == 0): the rows this rank sends to a peer
+__global__ void k_halo_pack(const float* __restrict__ src, const int* __restrict__ idx, int n, int width4,
+                            float* __restrict__ out) {
+    const long long total = (long long)n * width4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / width4), c = (int)(t % width4);
+        st4(out + ((size_t)k * width4 + c) * 4, ld4(src + ((size_t)idx[k] * width4 + c) * 4));
     }
 }
 
@@ -504,10 +519,19 @@ extern "C" int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const flo
     return 0;
 }
 
+int nn_node_aggregate_fwd_rows(const nn_nbr* nl, int n_rows, const float* msg, const float* e1, const float* e2,
+                               const float* unit, const float* a_in, const float* f_in, float* a_out, float* f_out,
+                               bool first, cudaStream_t s);
 extern "C" int nn_node_aggregate_fwd(const nn_nbr* nl, const float* msg, const float* e1, const float* e2,
                                      const float* unit, const float* a_in, const float* f_in, float* a_out,
                                      float* f_out, int32_t first_layer, void* stream) {
-    const int N = nl->n_atoms;
+    return nn_node_aggregate_fwd_rows(nl, nl->n_atoms, msg, e1, e2, unit, a_in, f_in, a_out, f_out, first_layer != 0,
+                                      (cudaStream_t)stream);
+}
+int nn_node_aggregate_fwd_rows(const nn_nbr* nl, int n_rows, const float* msg, const float* e1, const float* e2,
+                               const float* unit, const float* a_in, const float* f_in, float* a_out, float* f_out,
+                               bool first_layer, cudaStream_t stream) {
+    const int N = n_rows;
     if (N <= 0) return 0;
     int grid = nn_ceil_div(N, kWarps);
     if (first_layer) {
@@ -530,33 +554,53 @@ extern "C" int nn_equiv_update_fwd(const float* a_in, const float* f, const floa
     return 0;
 }
 
+int nn_energy_head_fwd_rows(const float* h2pre, const float* w3, const float* b3, const float* scale, const float* shift,
+                            const int64_t* z, const int32_t* sys_ptr, int n_rows, int n_systems, float* e_atom,
+                            float* energy, cudaStream_t s);
 extern "C" int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* b3, const float* scale,
                                   const float* shift, const int64_t* z, const int32_t* sys_ptr, int32_t n_atoms,
                                   int32_t n_systems, float* e_atom, float* energy, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+    return nn_energy_head_fwd_rows(h2pre, w3, b3, scale, shift, z, sys_ptr, n_atoms, n_systems, e_atom, energy,
+                                   (cudaStream_t)stream);
+}
+int nn_energy_head_fwd_rows(const float* h2pre, const float* w3, const float* b3, const float* scale, const float* shift,
+                            const int64_t* z, const int32_t* sys_ptr, int n_atoms, int n_systems, float* e_atom,
+                            float* energy, cudaStream_t s) {
     if (n_atoms > 0) {
         k_energy_atom<<<nn_ceil_div(n_atoms, kWarps), kThreads, 0, s>>>(h2pre, w3, b3, scale, shift, z, n_atoms, e_atom); NN_LAUNCHED(1);
     }
-    k_energy_sum<<<n_systems, kThreads, 0, s>>>(e_atom, sys_ptr, energy); NN_LAUNCHED(1);
+    k_energy_sum<<<n_systems, kThreads, 0, s>>>(e_atom, sys_ptr, n_atoms, energy); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_energy_head_fwd");
     return 0;
 }
 
-extern "C" int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
-                                      float* stress, void* workspace, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    const int N = nl->n_atoms;
+int nn_force_virial_rows(const nn_nbr* nl, int n_rows, const float* disp_bar, float* forces, float* virial, float* stress,
+                         void* workspace, cudaStream_t s) {
     float* vir_atom = virial ? (float*)workspace : nullptr;
     NN_REQUIRE(!virial || workspace, "virial needs a workspace of n_atoms*9 floats");
-    if (N > 0) {
-        k_force_virial_atom<<<nn_ceil_div(N, 128), 128, 0, s>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, disp_bar,
-                                                                 nl->pair_disp, nl->pos, nl->batch, nn_nbr_sysmeta(nl),
-                                                                 forces, vir_atom); NN_LAUNCHED(1);
+    if (n_rows > 0) {
+        k_force_virial_atom<<<nn_ceil_div(n_rows, 128), 128, 0, s>>>(nl->status, nl->row_ptr, nl->col, nl->edge_pair, n_rows,
+                                                                      disp_bar, nl->pair_disp, nl->pos, nl->batch,
+                                                                      nn_nbr_sysmeta(nl), forces, vir_atom); NN_LAUNCHED(1);
     }
     if (virial) {
-        k_virial_sum<<<nl->n_systems, kThreads, 0, s>>>(vir_atom, nl->sys_ptr, nl->cell, virial, stress); NN_LAUNCHED(1);
+        k_virial_sum<<<nl->n_systems, kThreads, 0, s>>>(vir_atom, nl->sys_ptr, n_rows, nl->cell, virial, stress); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("nn_force_virial_reduce");
+    return 0;
+}
+extern "C" int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
+                                      float* stress, void* workspace, void* stream) {
+    return nn_force_virial_rows(nl, nl->n_atoms, disp_bar, forces, virial, stress, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int nn_halo_pack(const float* src, const int32_t* idx, int32_t n, int32_t width, float* out, void* stream) {
+    NN_REQUIRE(width > 0 && width % 4 == 0, "width must be a positive multiple of 4");
+    if (n <= 0) return 0;
+    long long total = (long long)n * (width / 4);
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_halo_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(src, idx, n, width / 4, out); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_halo_pack");
     return 0;
 }
 
@@ -597,9 +641,9 @@ int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float*
     NN_CHECK_LAUNCH("pair_bwd_message");
     return 0;
 }
-int nn_node_aggregate_bwd_launch(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
-                                 float* mnbar, float* fbar_new, bool first, cudaStream_t s) {
-    const int N = nl->n_atoms;
+int nn_node_aggregate_bwd_launch(const nn_nbr* nl, int n_rows, const float* t, const float* mn, const float* e2,
+                                 const float* dfb, float* mnbar, float* fbar_new, bool first, cudaStream_t s) {
+    const int N = n_rows;
     if (N <= 0) return 0;
     int grid = nn_ceil_div(N, kWarps);
     if (first) {
