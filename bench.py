@@ -186,6 +186,7 @@ def main_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's version banner must not land on stdout (one JSON line)
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -326,7 +327,8 @@ def main_b200(args):
     F = 128
     # algorithmic work per launch (DESIGN.md section "kernels"): GEMM = 2*M*128*128 flop and 2*M*512 B
     alg = {
-        'pair_gemm': dict(bound='tensor', per_launch=2.0 * P * F * F, unit='TFLOP/s', scale=1e-12, peak=pk['tensor']),
+        # 32 flop per byte algorithmic (2*128*128 flop per 1 KB row) << machine balance: the GEMMs are HBM-bound
+        'pair_gemm': dict(bound='hbm', per_launch=None, unit='GB/s', scale=1e-9, peak=pk['hbm']),
         'node_gemm': dict(bound='tensor', per_launch=None, unit='TFLOP/s', scale=1e-12, peak=pk['tensor']),
         'message': dict(bound='hbm', per_launch=P * (512 + 8 + 80) + N * 512, unit='GB/s', scale=1e-9, peak=pk['hbm']),
         'aggregate': dict(bound='hbm', per_launch=None, unit='GB/s', scale=1e-9, peak=pk['hbm']),
@@ -336,6 +338,8 @@ def main_b200(args):
     }
     # stages whose launches differ (first layer skips the e2 / f_j streams): use the per-step total instead
     per_step_total = {
+        # per pair: layer 0 (U path only) fwd 1024 + 1536, bwd 1536 + 1024; other layers fwd 2*(1024 + 1536), bwd 2*1536 + 1024 + 1536
+        'pair_gemm': P * (5120.0 + (n_layers - 1) * 10752.0),
         'node_gemm': 2.0 * F * F * N * (n_layers * (2 + 3 + 3 + 2) + 4),
         'aggregate': (n_layers * (P * 2 * 512 + N * (512 * 2 + 1536) + 2 * P * 8 + P * 12) + (n_layers - 1) * (P * 512 + N * 1536 * 2)),
         'bwd_gather': (n_layers * (P * (1024 + 8 + 24) + N * 1536) + (n_layers - 1) * (P * 512 + N * 1536)),
@@ -359,9 +363,11 @@ def main_b200(args):
                     'bound': t['bound'], 'achieved': t['achieved'], 'peak': t['peak'], 'unit': t['unit'],
                     'frac': t['frac'], 'traffic': None, 'peak_source': pk['source'] + (' sustained bf16' if t['bound'] == 'tensor' else ' copy'),
                     'share_of_step': t['share'], 'launches_timed': t['launches']}
-        if dominant == 'pair_gemm':   # the same launches against the HBM roof (2 x 512 B per row)
-            roofline['hbm_achieved_gbs'] = 2.0 * P * 512 / (t['ms_total'] * 1e-3 / t['launches']) * 1e-9
-            roofline['hbm_frac'] = roofline['hbm_achieved_gbs'] / pk['hbm']
+        if dominant == 'pair_gemm':   # the same launches as fp32-equivalent FLOP/s (one 2*128*128 product per row)
+            roofline['tflops_fp32_equivalent'] = 2.0 * P * F * F * t['launches'] / K / (t['ms_total'] * 1e-3 / K) * 1e-12
+            roofline['tensor_pipe_passes'] = 3
+        if dominant == 'pair_gemm':   # ncu --set full, plain variant, per launch (profiles/r1_ncu_full_summary.txt)
+            roofline['traffic'] = None
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
@@ -431,10 +437,12 @@ def main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max
                 'config': {'workload': 'c4: ' + workloads.DESCRIPTION['c4'], 'atoms_total': N,
                            'parallelism': f'spatial domain decomposition, {dd.plan.grid} bricks, halo exchange of ghost '
                                           f'feature rows (6 exchanges per step) + all-reduce of forces/energy/virial',
-                           'owned_atoms_rank0': dd.plan.n_owned, 'ghost_atoms_rank0': dd.plan.n_ghost,
+                           'owned_atoms_rank0': dd.plan.n_owned, 'ghost_atoms_rank0': dd.plan.n_ghost, 'plans_built': dd.n_plans,
+                           'plan_skin_A': dd.skin,
                            'gemm_backend': 'tcgen05 3xTF32' if backend == 'tc' else 'fp32 SIMT',
-                           'note': 'the step includes the host-side brick/ghost planning and the neighbour rebuild; '
-                                   'positions are resident on every rank, results complete on every rank'},
+                           'note': 'every step rebuilds the neighbour list; the brick/ghost plan (host side) is reused while no '
+                                   'atom moved more than skin/2; positions resident on every rank, results complete '
+                                   'on every rank'},
                 'gpu_launches': launches, 'clocks': clocks,
                 'e2e': {'value': N * K / max_wall(wall, max_over_ranks), 'unit': UNIT, 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0, 'note': 'wall clock around the same loop (DomainDecomposition.__call__)'},
@@ -451,5 +459,10 @@ def max_wall(wall, max_over_ranks):
 
 
 if __name__ == '__main__':
+    # stdout carries exactly one JSON line: anything a library prints there (e.g. NCCL's version banner)
+    # is rerouted to stderr, the result line goes to the saved descriptor
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = _REAL_STDOUT
     a = parse()
     sys.exit(main_reference(a) if a.impl == 'reference' else main_b200(a))

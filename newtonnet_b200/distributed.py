@@ -165,14 +165,17 @@ class DomainDecomposition:
     -> CustomOutputSet with energy [1], gradient_force [N,3] (complete on every rank), stress, virial.
     """
 
-    def __init__(self, model, group=None, grid=None):
-        self.model, self.group, self.grid = model, group, grid
+    def __init__(self, model, group=None, grid=None, skin=1.0):
+        """skin (A): the brick/ghost plan is kept while no atom has moved more than skin/2 since it was
+        made (the ghost shell is cutoff + skin thick); the neighbour list itself is rebuilt every call."""
+        self.model, self.group, self.grid, self.skin = model, group, grid, float(skin)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.plan = None
         self._ws = None
-        self._cap_edges = 0
-        self.timings = {}
+        self._nl = None
+        self._state = None
+        self.n_plans = 0
 
     def _workspace(self, nbytes, device):
         if self._ws is None or self._ws.numel() < nbytes:
@@ -182,6 +185,17 @@ class DomainDecomposition:
     def _view(self, ws, ptr, rows, width):
         off = ptr - ws.data_ptr()
         return ws[off:off + rows * width * 4].view(torch.float32).view(rows, width)
+
+    def _replan(self, z, pos, cell3, cutoff, dev):
+        plan = HaloPlan(pos.detach().cpu().numpy(), cell3[0].detach().cpu().numpy(), self.rank, self.world,
+                        cutoff, self.grid, skin=self.skin)
+        self.plan = plan
+        self.n_plans += 1
+        l2g = torch.from_numpy(plan.local_to_global).to(dev)
+        self._state = dict(l2g=l2g, halo=HaloExchange(plan, dev, self.group), pos_ref=pos.detach().clone(),
+                           z_l=z.to(torch.int64)[l2g].contiguous(), n=pos.shape[0],
+                           batch_l=torch.zeros(len(plan.local_to_global), dtype=torch.int64, device=dev))
+        self._nl = None
 
     def __call__(self, z, pos, cell, want_virial=True):
         from newtonnet_b200.engine import NeighborList, _stream, get_engine
@@ -195,31 +209,43 @@ class DomainDecomposition:
         cell3 = cell.reshape(-1, 3, 3)
         if cell3.shape[0] != 1:
             raise ValueError('DomainDecomposition evaluates one periodic system')
-        plan = HaloPlan(pos.detach().cpu().numpy(), cell3[0].detach().cpu().numpy(), self.rank, self.world,
-                        pack.cutoff, self.grid)
-        self.plan = plan
-        halo = HaloExchange(plan, dev, self.group)
-        l2g = torch.from_numpy(plan.local_to_global).to(dev)
+        st = self._state
+        stale = st is None or st['n'] != N
+        if not stale:   # one scalar read-back decides whether the cached plan still covers the cutoff
+            moved = float((pos.detach() - st['pos_ref']).square().sum(1).max().sqrt())
+            flag = torch.tensor([1.0 if moved > 0.5 * self.skin else 0.0], device=dev)
+            if self.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            stale = bool(flag.item() > 0)
+        if stale:
+            self._replan(z, pos, cell3, pack.cutoff, dev)
+            st = self._state
+        plan, halo, l2g, z_l, batch_l = self.plan, st['halo'], st['l2g'], st['z_l'], st['batch_l']
         pos_l = pos.detach().to(torch.float32)[l2g].contiguous()
-        z_l = z.to(torch.int64)[l2g].contiguous()
         cell_l = cell3.detach().to(torch.float32).contiguous()
         n_local, n_owned = int(l2g.shape[0]), plan.n_owned
-        batch_l = torch.zeros(n_local, dtype=torch.int64, device=dev)
         s = _stream()
 
-        # ---- neighbour list over owned + ghost atoms (ghost-ghost pairs dropped)
+        # ---- neighbour list over owned + ghost atoms (ghost-ghost pairs dropped); capacities are kept
         def build(cap):
             nl = NeighborList(engine, pos_l, cell_l, batch_l, cap_edges=cap)
             nl.struct.n_owned = n_owned
+            return nl
+
+        def run_nbr(nl, fill=True):
             L.check(lib.nn_nbr_count(C.byref(nl.struct), pack.cutoff, s), 'nn_nbr_count')
-            if cap:
+            if fill:
                 L.check(lib.nn_nbr_fill(C.byref(nl.struct), pack.cutoff, s), 'nn_nbr_fill')
-            return nl, nl.check()
-        nl, st = build(self._cap_edges)
-        if self._cap_edges == 0 or st[L.ST_EDGE_OVERFLOW]:
-            self._cap_edges = int(st[L.ST_N_EDGES] * 1.08) + 64
-            self._cap_edges += self._cap_edges % 2
-            nl, st = build(self._cap_edges)
+
+        if self._nl is None:
+            probe = build(0)
+            run_nbr(probe, fill=False)
+            cap = int(probe.check()[L.ST_N_EDGES] * 1.08) + 64
+            self._nl = build(cap + cap % 2)
+        nl = self._nl
+        nl.rebind(pos_l, cell_l, batch_l)
+        nl.n_edges = None
+        run_nbr(nl)
         n_layers = pack.n_layers
 
         # ---- phased evaluation with halo exchanges
@@ -264,15 +290,19 @@ class DomainDecomposition:
         if self.world > 1:
             dist.all_reduce(forces, group=self.group)
             dist.all_reduce(red, group=self.group)
-        st = nl.check()
-        if st[L.ST_EDGE_OVERFLOW]:
-            raise RuntimeError('neighbour capacity overflow in the decomposed evaluation')
+        status = nl.check()
+        over = torch.tensor([float(status[L.ST_EDGE_OVERFLOW] != 0)], device=dev)
+        if self.world > 1:
+            dist.all_reduce(over, op=dist.ReduceOp.MAX, group=self.group)
+        if over.item() > 0:      # some rank's list outgrew its capacity: resize everywhere and repeat
+            self._nl = None
+            return self.__call__(z, pos, cell, want_virial)
         dt = pos.dtype
         out = CustomOutputSet(z=z, pos=pos, cell=cell, batch=torch.zeros(N, dtype=torch.int64, device=dev))
         out.energy = red[:1].to(dt)
         out.gradient_force = forces.to(dt)
         out.virial = red[1:10].reshape(1, 3, 3).to(dt)
         out.stress = red[10:19].reshape(1, 3, 3).to(dt)
-        out.n_owned, out.n_ghost, out.n_local_edges = n_owned, plan.n_ghost, st[L.ST_N_EDGES]
+        out.n_owned, out.n_ghost, out.n_local_edges = n_owned, plan.n_ghost, status[L.ST_N_EDGES]
         out._keep = (nl, z_l, pos_l, cell_l, batch_l, halo)
         return out
