@@ -96,24 +96,39 @@ __device__ __forceinline__ float4 edge_part(const float* __restrict__ s_wet, con
 }
 
 // Pairs are stored grouped by their lower atom i (pair_ptr), so one warp walks the forward pairs of one
-// atom: the i-side rows are loaded once per atom and only the j-side rows are gathered per pair.
+// atom: the i-side rows are loaded once per atom and only the j-side rows are gathered per pair.  The
+// pairs of an atom are contiguous, so their rbf rows are staged into shared memory with coalesced loads
+// (a chunk of pairs at a time) and the j-side gather of the next pair is issued before the current pair
+// is computed (software prefetch) - the kernels are latency-bound otherwise.
+constexpr int kMsgChunk = 32;
 __global__ void __launch_bounds__(kThreads, 3)
 k_edge_message_fwd(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
                    const float* __restrict__ rbf, const float* __restrict__ mn,
                    const float* __restrict__ Wet, float* __restrict__ msg) {
     __shared__ __align__(16) float s_wet[kNB * kF];
+    __shared__ __align__(16) float s_rbf[kWarps][kMsgChunk * kNB];
     for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* my_rbf = s_rbf[wid];
+    for (int i = blockIdx.x * kWarps + wid; i < N; i += gridDim.x * kWarps) {
         const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
         if (p0 >= p1) continue;
         const float4 a = ld4(mn + (size_t)i * kF + 4 * lane);
-        for (int p = p0; p < p1; ++p) {
-            const int j = pair_j[p];
-            float4 b = ld4(mn + (size_t)j * kF + 4 * lane);
-            float4 me = edge_part(s_wet, rbf + (size_t)p * kNB, lane);
-            st4(msg + (size_t)p * kF + 4 * lane, f4_mul(me, f4_mul(a, b)));
+        for (int c0 = p0; c0 < p1; c0 += kMsgChunk) {
+            const int n = min(kMsgChunk, p1 - c0);
+            const int my_j = lane < n ? pair_j[c0 + lane] : 0;
+            for (int t = lane; t < n * (kNB / 4); t += 32) st4(my_rbf + 4 * t, ld4(rbf + (size_t)c0 * kNB + 4 * t));
+            __syncwarp();
+            float4 b_next = ld4(mn + (size_t)__shfl_sync(0xffffffffu, my_j, 0) * kF + 4 * lane);
+            for (int t = 0; t < n; ++t) {
+                const float4 b = b_next;
+                const int jn = __shfl_sync(0xffffffffu, my_j, (t + 1) & 31);
+                if (t + 1 < n) b_next = ld4(mn + (size_t)jn * kF + 4 * lane);
+                float4 me = edge_part(s_wet, my_rbf + t * kNB, lane);
+                st4(msg + (size_t)(c0 + t) * kF + 4 * lane, f4_mul(me, f4_mul(a, b)));
+            }
+            __syncwarp();
         }
     }
 }
@@ -260,23 +275,33 @@ k_pair_bwd_gather(const int* __restrict__ pair_ptr, const int* __restrict__ pair
             const float* fi = f_in + (size_t)i * 3 * kF + 4 * lane;
             fix = ld4(fi); fiy = ld4(fi + kF); fiz = ld4(fi + 2 * kF);
         }
-        for (int p = p0; p < p1; ++p) {
+        // software prefetch: the rows of pair p+1 are requested before pair p is reduced
+        float4 ndx, ndy, ndz, nfx = f4_zero(), nfy = f4_zero(), nfz = f4_zero(), nv1;
+        auto fetch = [&](int p) {
             const int j = pair_j[p];
             const float* dj = dfb + (size_t)j * 3 * kF + 4 * lane;
-            const float4 djx = ld4(dj), djy = ld4(dj + kF), djz = ld4(dj + 2 * kF);
+            ndx = ld4(dj); ndy = ld4(dj + kF); ndz = ld4(dj + 2 * kF);
+            if (!FIRST) {
+                const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
+                nfx = ld4(fj); nfy = ld4(fj + kF); nfz = ld4(fj + 2 * kF);
+            }
+            nv1 = ld4(e1_io + (size_t)p * kF + 4 * lane);
+        };
+        fetch(p0);
+        for (int p = p0; p < p1; ++p) {
+            const float4 djx = ndx, djy = ndy, djz = ndz, fjx = nfx, fjy = nfy, fjz = nfz, v1 = nv1;
+            if (p + 1 < p1) fetch(p + 1);
             const float4 wx = f4_sub(dix, djx), wy = f4_sub(diy, djy), wz = f4_sub(diz, djz);
             const float ux = unit[3 * p], uy = unit[3 * p + 1], uz = unit[3 * p + 2];
             const size_t po = (size_t)p * kF + 4 * lane;
-            const float4 v1 = ld4(e1_io + po);
             float sx = warp_sum(f4_dot(wx, v1)), sy = warp_sum(f4_dot(wy, v1)), sz = warp_sum(f4_dot(wz, v1));
             if (lane == 0) { ubar[3 * p] += sx; ubar[3 * p + 1] += sy; ubar[3 * p + 2] += sz; }
             float4 e1b = f4_zero();
             e1b = f4_fma(ux, wx, e1b); e1b = f4_fma(uy, wy, e1b); e1b = f4_fma(uz, wz, e1b);
             st4(e1_io + po, e1b);
             if (!FIRST) {
-                const float* fj = f_in + (size_t)j * 3 * kF + 4 * lane;
-                float4 acc = f4_mul(dix, ld4(fj));
-                acc = f4_fma(diy, ld4(fj + kF), acc); acc = f4_fma(diz, ld4(fj + 2 * kF), acc);
+                float4 acc = f4_mul(dix, fjx);
+                acc = f4_fma(diy, fjy, acc); acc = f4_fma(diz, fjz, acc);
                 acc = f4_fma(djx, fix, acc); acc = f4_fma(djy, fiy, acc); acc = f4_fma(djz, fiz, acc);
                 st4(e2bar + po, acc);
             }
@@ -287,41 +312,66 @@ k_pair_bwd_gather(const int* __restrict__ pair_ptr, const int* __restrict__ pair
 // mtot = mbar + abar_i + abar_j;  y = mtot * mn_i * mn_j;  xbar_p += <y, We drbf_p>  (one warp reduction:
 // dE/dx is contracted with We here, instead of keeping a 20-wide rbf gradient per pair);
 // t = mtot * (We rbf_p)  (overwrites mbar)
+constexpr int kBwdChunk = 16;
 __global__ void __launch_bounds__(kThreads, 3)
 k_pair_bwd_message(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
                    const float* __restrict__ abar, const float* __restrict__ mn,
                    const float* __restrict__ rbf, const float* __restrict__ drbf, const float* __restrict__ Wet,
                    float* __restrict__ mbar_io, float* __restrict__ x_bar) {
     __shared__ __align__(16) float s_wet[kNB * kF];
+    __shared__ __align__(16) float s_r[kWarps][kBwdChunk * kNB];
+    __shared__ __align__(16) float s_d[kWarps][kBwdChunk * kNB];
     for (int k = threadIdx.x; k < kNB * kF; k += kThreads) s_wet[k] = Wet[k];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* my_r = s_r[wid];
+    float* my_d = s_d[wid];
+    for (int i = blockIdx.x * kWarps + wid; i < N; i += gridDim.x * kWarps) {
         const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
         if (p0 >= p1) continue;
         const float4 ab_i = ld4(abar + (size_t)i * kF + 4 * lane);
         const float4 mn_i = ld4(mn + (size_t)i * kF + 4 * lane);
-        for (int p = p0; p < p1; ++p) {
-            const int j = pair_j[p];
-            const size_t po = (size_t)p * kF + 4 * lane;
-            float4 mt = f4_add(ld4(mbar_io + po), f4_add(ab_i, ld4(abar + (size_t)j * kF + 4 * lane)));
-            const float4 y = f4_mul(mt, f4_mul(mn_i, ld4(mn + (size_t)j * kF + 4 * lane)));
-            // me = We rbf_p and dme = We drbf_p share the We loads
-            float4 me = f4_zero(), dme = f4_zero();
-            const float* r = rbf + (size_t)p * kNB;
-            const float* dr = drbf + (size_t)p * kNB;
-#pragma unroll 1
-            for (int q = 0; q < kNB / 4; ++q) {
-                const float4 rv = ld4(r + 4 * q), dv = ld4(dr + 4 * q);
-                float4 w;
-                w = ld4(s_wet + (4 * q + 0) * kF + 4 * lane); me = f4_fma(rv.x, w, me); dme = f4_fma(dv.x, w, dme);
-                w = ld4(s_wet + (4 * q + 1) * kF + 4 * lane); me = f4_fma(rv.y, w, me); dme = f4_fma(dv.y, w, dme);
-                w = ld4(s_wet + (4 * q + 2) * kF + 4 * lane); me = f4_fma(rv.z, w, me); dme = f4_fma(dv.z, w, dme);
-                w = ld4(s_wet + (4 * q + 3) * kF + 4 * lane); me = f4_fma(rv.w, w, me); dme = f4_fma(dv.w, w, dme);
+        for (int c0 = p0; c0 < p1; c0 += kBwdChunk) {
+            const int n = min(kBwdChunk, p1 - c0);
+            const int my_j = lane < n ? pair_j[c0 + lane] : 0;
+            for (int t = lane; t < n * (kNB / 4); t += 32) {
+                st4(my_r + 4 * t, ld4(rbf + (size_t)c0 * kNB + 4 * t));
+                st4(my_d + 4 * t, ld4(drbf + (size_t)c0 * kNB + 4 * t));
             }
-            const float xs = warp_sum(f4_dot(y, dme));
-            if (lane == 0) x_bar[p] += xs;
-            st4(mbar_io + po, f4_mul(mt, me));
+            __syncwarp();
+            float4 n_m, n_ab, n_mn;
+            {
+                const int j0 = __shfl_sync(0xffffffffu, my_j, 0);
+                n_m = ld4(mbar_io + (size_t)c0 * kF + 4 * lane);
+                n_ab = ld4(abar + (size_t)j0 * kF + 4 * lane); n_mn = ld4(mn + (size_t)j0 * kF + 4 * lane);
+            }
+            for (int t = 0; t < n; ++t) {
+                const size_t po = (size_t)(c0 + t) * kF + 4 * lane;
+                const float4 mt = f4_add(n_m, f4_add(ab_i, n_ab));
+                const float4 y = f4_mul(mt, f4_mul(mn_i, n_mn));
+                const int jn = __shfl_sync(0xffffffffu, my_j, (t + 1) & 31);
+                if (t + 1 < n) {
+                    n_m = ld4(mbar_io + po + kF);
+                    n_ab = ld4(abar + (size_t)jn * kF + 4 * lane); n_mn = ld4(mn + (size_t)jn * kF + 4 * lane);
+                }
+                // me = We rbf_p and dme = We drbf_p share the We loads
+                float4 me = f4_zero(), dme = f4_zero();
+                const float* r = my_r + t * kNB;
+                const float* dr = my_d + t * kNB;
+#pragma unroll
+                for (int q = 0; q < kNB / 4; ++q) {
+                    const float4 rv = ld4(r + 4 * q), dv = ld4(dr + 4 * q);
+                    float4 w;
+                    w = ld4(s_wet + (4 * q + 0) * kF + 4 * lane); me = f4_fma(rv.x, w, me); dme = f4_fma(dv.x, w, dme);
+                    w = ld4(s_wet + (4 * q + 1) * kF + 4 * lane); me = f4_fma(rv.y, w, me); dme = f4_fma(dv.y, w, dme);
+                    w = ld4(s_wet + (4 * q + 2) * kF + 4 * lane); me = f4_fma(rv.z, w, me); dme = f4_fma(dv.z, w, dme);
+                    w = ld4(s_wet + (4 * q + 3) * kF + 4 * lane); me = f4_fma(rv.w, w, me); dme = f4_fma(dv.w, w, dme);
+                }
+                const float xs = warp_sum(f4_dot(y, dme));
+                if (lane == 0) x_bar[c0 + t] += xs;
+                st4(mbar_io + po, f4_mul(mt, me));
+            }
+            __syncwarp();
         }
     }
 }
