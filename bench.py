@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
     ap.add_argument('--backend', default=os.environ.get('NN_GEMM_BACKEND', 'auto'), choices=['auto', 'simt', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -216,6 +216,8 @@ def main_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     if args.workload == 'c4' and world > 1:
         return main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max_over_ranks)
+    if args.workload == 'c5':
+        return main_c5_training(args, world, rank, local, dev, lib, backend, barrier, max_over_ranks, sum_over_ranks)
     z_h, pos_h, cell_h, batch_h = workloads.make(args.workload, seed=rank)
     N, B = len(z_h), cell_h.shape[0]
     stress = args.workload in ('c3', 'c4')
@@ -451,6 +453,57 @@ def main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max
     else:
         max_wall(wall, max_over_ranks)
     dist.destroy_process_group()
+    return 0
+
+
+def main_c5_training(args, world, rank, local, dev, lib, backend, barrier, max_over_ranks, sum_over_ranks):
+    """config 5: training step (energy + force loss, double backward, Adam) on MD17-shaped synthetic data,
+    100 molecules x 21 atoms per GPU, data-parallel gradient all-reduce (one flat 1.6 MB bucket)."""
+    import torch
+    import torch.distributed as dist
+    from newtonnet_b200 import workloads
+    from newtonnet_b200.train import training_step
+    K, W = args.steps, max(args.warmup, 3)
+    z, pos, cell, batch = workloads.make('c1', seed=rank)
+    N = len(z)
+    rng = np.random.default_rng(7 + rank)
+    t = lambda a: torch.tensor(a, device=dev)
+    e_t, f_t = t(rng.standard_normal(cell.shape[0]).astype(np.float32)), t(rng.standard_normal(pos.shape).astype(np.float32))
+    model = seed0_weights().to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    args_t = (t(z), t(pos), t(cell), t(batch), e_t, f_t)
+    for _ in range(W):
+        loss = training_step(model, opt, *args_t)
+    lib.nn_launch_count(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(); torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        loss = training_step(model, opt, *args_t)
+    ev1.record()
+    torch.cuda.synchronize(); barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    atoms_all = sum_over_ranks(float(N))
+    launches = int(lib.nn_launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        v = atoms_all * K / (dev_ms * 1e-3)
+        print(json.dumps({'metric': 'training ' + METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+                          'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                          'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': 'c5: training step, 100 x 21 atoms per GPU, loss MSE(E) + 50 MSE(F), '
+                                                 'double backward, clip 1.0, Adam 1e-3', 'atoms_per_gpu': N,
+                                     'parallelism': f'dp{world}, one all-reduce of a flat 401,155-float gradient bucket',
+                                     'final_loss': float(loss)},
+                          'gpu_launches': launches, 'clocks': clocks,
+                          'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                                  'note': 'training data resident on the device'},
+                          'roofline': None, 'cpu_baseline': None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

@@ -248,6 +248,17 @@ NN_API int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* 
 NN_API int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
                            float* stress, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------ training-path primitives (row T)
+ * Closed under differentiation together with nn_gemm128 and nn_halo_pack (= gather rows), so autograd can
+ * compose the double backward of reference train/trainer.py:303-313. */
+/* out[i,:] = sum over k in [row_ptr[i], row_ptr[i+1]) of src[perm ? perm[k] : k, :]  (fixed order) - the
+ * deterministic form of torch_geometric.utils.scatter(reduce='sum') (models/newtonnet.py:214,226). */
+NN_API int nn_segment_sum(const float* src, const int32_t* perm, const int32_t* row_ptr, int32_t n_rows,
+                          int32_t width, float* out, void* stream);
+/* out[128,128] = X[m,128]^T @ Y[m,128]  (weight gradients of the 128x128 linears). */
+NN_API size_t nn_gemm128_tn_workspace_bytes(int32_t m);
+NN_API int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,9 @@ SYMBOLS = {
     'nn_eval_phase': (C.c_int, [C.POINTER(EvalArgs), C.c_int32, C.c_int32, _fp]),
     'nn_eval_buffer': (C.c_void_p, [C.POINTER(EvalArgs), C.c_int32, C.c_int32]),
     'nn_halo_pack': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
+    'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
     'nn_edge_message_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp]),

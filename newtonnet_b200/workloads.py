@@ -72,4 +72,5 @@ DESCRIPTION = {
     'c2': 'ANI-1x-shaped ragged batch, 4096 molecules of 4..64 atoms per GPU, energy+forces',
     'c3': 'periodic water box, 3000 atoms (L=31.04 A), neighbour rebuild + energy+forces+stress',
     'c4': 'periodic water box, 98304 atoms (L=99.33 A), neighbour rebuild + energy+forces+stress',
+    'c5': 'training step on MD17-shaped batches, 21 atoms x 100 molecules per GPU',
 }

@@ -385,6 +385,36 @@ def forward_analytic(sd, z, pos, cell, batch, dtype=torch.float64, cutoff=CUTOFF
     return out
 
 
+# ----------------------------------------------------------------------------- row T: training step
+def training_gradients(sd, z, pos, cell, batch, e_target, f_target, force_weight=50.0, dtype=torch.float64,
+                       cutoff=CUTOFF):
+    """Loss and parameter gradients of one training step: forward with create_graph=True
+    (models/newtonnet.py:106-113, models/output.py:66-73), loss = MSE(E) + w MSE(F) (train/loss.py:48,
+    104-138), loss.backward() (train/trainer.py:310) - the double backward through the force graph.
+    Returns (loss, {parameter name: gradient ndarray})."""
+    params = {k: torch.as_tensor(np.asarray(v)).to(dtype).requires_grad_(k.split('.')[-1] != 'frequencies')
+              for k, v in sd.items()}
+    z = torch.as_tensor(np.asarray(z)).long()
+    batch = torch.as_tensor(np.asarray(batch)).long()
+    pos = torch.as_tensor(np.asarray(pos)).to(dtype).clone().requires_grad_(True)
+    cell = torch.as_tensor(np.asarray(cell)).to(dtype)
+    n_sys = cell.shape[0]
+    rbf, direction, edge_index = edge_embedding(params, pos, cell, batch, cutoff)
+    a = torch.nn.functional.embedding(z, params['embedding_layers.node_embedding.weight'], padding_idx=0)
+    f = torch.zeros(z.shape[0], 3, a.shape[1], dtype=dtype)
+    for l in range(n_layers(sd)):
+        a, f = interaction(params, l, a, f, direction, rbf, edge_index)
+    energy = _segment_sum(atomic_energy(params, a, z), batch, n_sys).reshape(-1)
+    g_pos, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=True)
+    e_t = torch.as_tensor(np.asarray(e_target)).to(dtype)
+    f_t = torch.as_tensor(np.asarray(f_target)).to(dtype)
+    loss = torch.mean((energy - e_t) ** 2) + force_weight * torch.mean((-g_pos - f_t) ** 2)
+    names = [k for k, v in params.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
+    out = {k: (np.zeros(params[k].shape) if g is None else g.detach().numpy()) for k, g in zip(names, grads)}
+    return float(loss), out
+
+
 # ----------------------------------------------------------------------------- synthetic workloads
 def water_box(nside, seed=0):
     """Synthetic periodic water lattice of SURVEY.md §8d C3/C4 (numpy restatement of the generator in

@@ -295,5 +295,32 @@ def main():
     save_case('mols256', 'seed0', sd_seed0, EF, z, p, c, b)
 
 
+def training_golden():
+    """Row T: one training step's loss and parameter gradients from the unmodified reference in train mode
+    (create_graph=True on the force head, reference models/newtonnet.py:106-113; loss = MSE(E) + w MSE(F),
+    train/loss.py:48,104-138; weights 1 / 50, scripts/config.yml:46-51), fp64."""
+    sd_seed0 = dict(np.load(f'{OUT}/weights_seed0.npz'))
+    for name, (z, p, c, b) in {'mols24': molecule_batch(24, seed=1), 'water81': water_box(3)}.items():
+        m = build_model(sd_seed0, ['energy', 'gradient_force'], torch.float64)
+        m.train()
+        g = torch.Generator().manual_seed(11)
+        e_t = torch.randn(c.shape[0], generator=g, dtype=torch.float64)
+        f_t = torch.randn(p.shape[0], 3, generator=g, dtype=torch.float64)
+        out = m(z, p.double().clone(), c.double(), b)
+        loss = torch.nn.MSELoss()(out.energy, e_t) + 50.0 * torch.nn.MSELoss()(out.gradient_force, f_t)
+        loss.backward()
+        d = dict(z=z.numpy(), pos=p.numpy().astype(np.float32), cell=c.numpy().astype(np.float32), batch=b.numpy(),
+                 e_target=e_t.numpy(), f_target=f_t.numpy(), loss=loss.item(), force_weight=50.0)
+        for k, v in m.named_parameters():
+            d['grad.' + k] = np.zeros(v.shape) if v.grad is None else v.grad.numpy()
+        np.savez_compressed(f'{OUT}/train_{name}.npz', **d)
+        gn = np.sqrt(sum((d[k] ** 2).sum() for k in d if k.startswith('grad.')))
+        print(f'train_{name}: loss {loss.item():.6f} |grad| {gn:.4f}')
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+        training_golden()
+    else:
+        main()
+        training_golden()

@@ -94,3 +94,27 @@ def test_shard_batch_balanced_partition():
             seen.append((sl.start, sl.stop)); atoms.append(len(zr))
         assert seen[0][0] == 0 and seen[-1][1] == 257 and all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
         assert sum(atoms) == len(z) and max(atoms) - min(atoms) <= 64 * 2
+
+
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from newtonnet_b200.train import allreduce_gradients
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)),
+                  torch.nn.Parameter(torch.randn(2, 2), requires_grad=False), torch.nn.Parameter(torch.randn(4))]
+        params[0].grad = torch.full((5, 3), float(rank + 1))
+        params[1].grad = torch.arange(7.0) * (rank + 1)
+        # params[3] has no gradient on any rank (like the dead layer-0 equiv_message2): reduced as zeros
+        flat = allreduce_gradients(params)
+        assert flat.numel() == 15 + 7 + 4
+        assert torch.allclose(params[0].grad, torch.full((5, 3), 1.5))
+        assert torch.allclose(params[1].grad, torch.arange(7.0) * 1.5)
+        assert params[2].grad is None and torch.equal(params[3].grad, torch.zeros(4))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    mp.spawn(_grad_worker, args=(2, _free_port()), nprocs=2, join=True)

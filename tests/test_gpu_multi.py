@@ -102,3 +102,46 @@ def test_sharded_molecule_batch_matches_unsharded(tmp_path):
     e = np.concatenate([np.load(tmp_path / f'r{r}.npz')['e'] for r in range(world)])
     f = np.concatenate([np.load(tmp_path / f'r{r}.npz')['f'] for r in range(world)])
     assert np.array_equal(e, ref['e']) and np.array_equal(f, ref['f'])     # independent systems: bit identical
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from newtonnet_b200.distributed import shard_batch
+        from newtonnet_b200.train import allreduce_gradients
+        from newtonnet_b200 import workloads
+        z, pos, cell, batch = workloads.molecule_batch(16, seed=4)
+        rng = np.random.default_rng(1)
+        e_t, f_t = rng.standard_normal(16).astype(np.float32), rng.standard_normal(pos.shape).astype(np.float32)
+        t = lambda a: torch.tensor(a, device=dev)
+
+        def grads_of(r):
+            zr, pr, cr, br, sl = shard_batch(z, pos, cell, batch, r, world)
+            a0 = int((batch < sl.start).sum()); a1 = a0 + len(zr)
+            model = _model(dev, ['energy', 'gradient_force'])
+            model.train()
+            out = model(t(zr), t(pr).requires_grad_(True), t(cr), t(br))
+            loss = torch.nn.functional.mse_loss(out.energy, t(e_t[sl])) + \
+                50.0 * torch.nn.functional.mse_loss(out.gradient_force, t(f_t[a0:a1]))
+            loss.backward()
+            return model
+
+        mine = grads_of(rank)
+        allreduce_gradients(mine.parameters())
+        every = [grads_of(r) for r in range(world)]
+        for (k, p), *others in zip(mine.named_parameters(), *[m.named_parameters() for m in every]):
+            if not p.requires_grad:
+                continue
+            want = sum((q.grad if q.grad is not None else torch.zeros_like(q)) for _, q in others) / world
+            assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-6 * max(1.0, float(want.abs().max()))), k
+        dist.barrier(device_ids=[rank])
+    finally:
+        dist.destroy_process_group()
+
+
+@needs2
+def test_data_parallel_gradient_allreduce(tmp_path):
+    mp.spawn(_train_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)

@@ -99,3 +99,18 @@ def test_synthetic_generators():
     assert 50 < ei.shape[1] / 3000 < 58
     z, pos, cell, batch = O.molecule_batch(64)
     assert batch.max() == 63 and np.all(np.diff(batch) >= 0)
+
+
+@pytest.mark.parametrize('name', ['mols24', 'water81'])
+def test_training_gradients_match_reference(name):
+    """Row T: loss and parameter gradients of one training step (double backward through the forces)
+    against the unmodified reference in train mode (tests/golden/train_*.npz)."""
+    d = dict(np.load(f'{GOLDEN}/train_{name}.npz'))
+    w = load_weights('seed0')
+    loss, g = O.training_gradients(w, d['z'], d['pos'], d['cell'], d['batch'], d['e_target'], d['f_target'],
+                                   float(d['force_weight']))
+    assert abs(loss - float(d['loss'])) < 1e-9 * abs(float(d['loss']))
+    for k, v in g.items():
+        assert np.abs(v - d['grad.' + k]).max() < 1e-9 * max(1.0, np.abs(d['grad.' + k]).max()), k
+    # the dead layer-0 equiv_message2 gets exactly zero gradient (SURVEY 8a row T)
+    assert np.abs(d['grad.interaction_layers.0.equiv_message2.0.weight']).max() == 0.0
