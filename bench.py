@@ -408,7 +408,7 @@ def main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max
     N = len(z_h)
     model = seed0_weights().to(dev)
     model.eval()
-    dd = DomainDecomposition(model)
+    dd = DomainDecomposition(model, transport=os.environ.get('NN_DD_TRANSPORT', 'p2p'))
     rng = np.random.default_rng(100)
     steps_pos = [(pos_h + rng.normal(0, 0.01, pos_h.shape)).astype(np.float32) for _ in range(K + W)]
     z_d = torch.tensor(z_h, device=dev); cell_d = torch.tensor(cell_h, device=dev)
@@ -438,7 +438,9 @@ def main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max
                 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': 'c4: ' + workloads.DESCRIPTION['c4'], 'atoms_total': N,
                            'parallelism': f'spatial domain decomposition, {dd.plan.grid} bricks, halo exchange of ghost '
-                                          f'feature rows (6 exchanges per step) + all-reduce of forces/energy/virial',
+                                          f'feature rows (6 exchanges per step, transport {dd.transport}: '
+                                          f'{"pack kernel storing into peer memory over NVLink" if dd.transport == "p2p" else "pack kernel + NCCL all_to_all"}) '
+                                          f'+ all-reduce of forces/energy/virial',
                            'owned_atoms_rank0': dd.plan.n_owned, 'ghost_atoms_rank0': dd.plan.n_ghost, 'plans_built': dd.n_plans,
                            'plan_skin_A': dd.skin,
                            'gemm_backend': 'tcgen05 3xTF32' if backend == 'tc' else 'fp32 SIMT',

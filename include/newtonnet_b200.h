@@ -248,6 +248,24 @@ NN_API int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* 
 NN_API int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
                            float* stress, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------ halo exchange over NVLink peer memory
+ * The pack kernel stores the rows a rank owes its peers directly into the peers' landing buffers (P2P
+ * stores through NVSwitch) and then raises flag[my_rank] = epoch in each peer's flag array; nn_halo_wait
+ * spins (bounded) on the local flags.  Buffers come from nn_p2p_alloc (plain cudaMalloc, zero-filled) so
+ * that CUDA IPC handles (64 bytes, exchanged by the caller) can map them into the other processes. */
+NN_API int nn_p2p_alloc(size_t bytes, void** ptr);
+NN_API int nn_p2p_free(void* ptr);
+NN_API int nn_p2p_get_handle(void* ptr, void* handle64);
+NN_API int nn_p2p_open_handle(const void* handle64, void** ptr);
+NN_API int nn_p2p_close_handle(void* ptr);
+NN_API int nn_halo_push(const float* src, const int32_t* send_idx, int32_t width, int32_t n_peers,
+                        float* const* landing, int32_t* const* flags, const int32_t* row_offset,
+                        const int32_t* send_begin, const int32_t* send_end, int32_t my_rank, int32_t epoch,
+                        uint32_t* done_counter, void* stream);
+NN_API int nn_copy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+NN_API int nn_halo_wait(int32_t* flags, const int32_t* expect, int32_t world, int32_t epoch, int32_t* status,
+                        void* stream);
+
 /* ------------------------------------------------------------------ training-path primitives (row T)
  * Closed under differentiation together with nn_gemm128 and nn_halo_pack (= gather rows), so autograd can
  * compose the double backward of reference train/trainer.py:303-313. */

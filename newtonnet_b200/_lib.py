@@ -79,6 +79,14 @@ SYMBOLS = {
     'nn_eval_phase': (C.c_int, [C.POINTER(EvalArgs), C.c_int32, C.c_int32, _fp]),
     'nn_eval_buffer': (C.c_void_p, [C.POINTER(EvalArgs), C.c_int32, C.c_int32]),
     'nn_halo_pack': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    'nn_p2p_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    'nn_p2p_free': (C.c_int, [_fp]),
+    'nn_p2p_get_handle': (C.c_int, [_fp, _fp]),
+    'nn_p2p_open_handle': (C.c_int, [_fp, C.POINTER(C.c_void_p)]),
+    'nn_p2p_close_handle': (C.c_int, [_fp]),
+    'nn_halo_push': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    'nn_copy_d2d': (C.c_int, [_fp, _fp, C.c_size_t, _fp]),
+    'nn_halo_wait': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),

@@ -98,14 +98,17 @@ class HaloPlan:
         local_of[self.owned] = np.arange(self.n_owned)
         send = []
         self.send_counts = []
+        self.send_row_offset = []        # first row of this rank's block in peer s's ghost order
         for s in range(world):
             if s == rank:
                 self.send_counts.append(0)
+                self.send_row_offset.append(0)
                 continue
             gs = ghosts_of(s)
             mine = gs[owner[gs] == rank]
             send.append(local_of[mine])
             self.send_counts.append(len(mine))
+            self.send_row_offset.append(int((owner[gs] < rank).sum()))
         self.send_index = np.concatenate(send).astype(np.int32) if send else np.zeros(0, np.int32)
 
 
@@ -158,6 +161,101 @@ class HaloExchange:
                 req.wait()
 
 
+class PeerHaloExchange:
+    """Owner -> ghost copy over NVLink peer memory (csrc/p2p.cu): the pack kernel stores rows directly into
+    the peers' landing buffers and raises per-source flags; the receiver spins on its flags and copies
+    its landing buffer into the ghost tail.  No NCCL call on the data path.  Collective: every rank of
+    the group must construct it (and call `exchange`) in the same order."""
+
+    MAX_WIDTH = 3 * L.NN_F
+
+    def __init__(self, plan, device, group=None):
+        self.plan, self.group, self.device = plan, group, torch.device(device)
+        self.lib = L.load()
+        self.rank, self.world = plan.rank, plan.world
+        self.epoch = 0
+        self.send_index = torch.from_numpy(plan.send_index).to(self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.done = torch.zeros(1, **i32)
+        self.status = torch.zeros(1, **i32)
+        self.expect = torch.tensor([1 if c > 0 else 0 for c in plan.recv_counts], **i32)
+        nbytes = max(plan.n_ghost, 1) * self.MAX_WIDTH * 4
+        self.local = []
+        for _ in range(3):           # two landing buffers (epoch parity) and the flag array
+            p = C.c_void_p()
+            L.check(self.lib.nn_p2p_alloc(nbytes if len(self.local) < 2 else 4 * max(self.world, 1), C.byref(p)), 'nn_p2p_alloc')
+            self.local.append(p.value)
+        handles = []
+        for p in self.local:
+            h = C.create_string_buffer(64)
+            L.check(self.lib.nn_p2p_get_handle(p, h), 'nn_p2p_get_handle')
+            handles.append(h.raw)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.peers = [s for s in range(self.world) if s != self.rank and plan.send_counts[s] > 0]
+        self.opened = {}
+        for s in range(self.world):
+            if s == self.rank or (plan.send_counts[s] == 0):
+                continue
+            ptrs = []
+            for raw in gathered[s]:
+                q = C.c_void_p()
+                L.check(self.lib.nn_p2p_open_handle(C.create_string_buffer(raw, 64), C.byref(q)), 'nn_p2p_open_handle')
+                ptrs.append(q.value)
+            self.opened[s] = ptrs
+        n = len(self.peers)
+        begins, ends, off = [], [], 0
+        counts_nonself = [(s, plan.send_counts[s]) for s in range(self.world) if s != self.rank]
+        pos = {}
+        for s, c in counts_nonself:      # send_index is ordered by destination rank
+            pos[s] = (off, off + c)
+            off += c
+        self._arrays = []
+        for par in range(2):
+            landing = (C.c_void_p * max(n, 1))(*[self.opened[s][par] for s in self.peers])
+            flags = (C.c_void_p * max(n, 1))(*[self.opened[s][2] for s in self.peers])
+            self._arrays.append((landing, flags))
+        self._row_offset = (C.c_int32 * max(n, 1))(*[plan.send_row_offset[s] for s in self.peers])
+        self._begin = (C.c_int32 * max(n, 1))(*[pos[s][0] for s in self.peers])
+        self._end = (C.c_int32 * max(n, 1))(*[pos[s][1] for s in self.peers])
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def exchange(self, rows):
+        p = self.plan
+        if p.world == 1:
+            return
+        self.epoch += 1
+        par = self.epoch & 1
+        width = rows.shape[1]
+        s = torch.cuda.current_stream().cuda_stream
+        if self.peers:
+            landing, flags = self._arrays[par]
+            L.check(self.lib.nn_halo_push(rows.data_ptr(), self.send_index.data_ptr(), width, len(self.peers), landing, flags,
+                                          self._row_offset, self._begin, self._end, self.rank, self.epoch,
+                                          self.done.data_ptr(), s), 'nn_halo_push')
+        if p.n_ghost:
+            L.check(self.lib.nn_halo_wait(self.local[2], self.expect.data_ptr(), self.world, self.epoch,
+                                          self.status.data_ptr(), s), 'nn_halo_wait')
+            L.check(self.lib.nn_copy_d2d(rows[p.n_owned:].data_ptr(), self.local[par], p.n_ghost * width * 4, s), 'nn_copy_d2d')
+
+    def check(self):
+        st = int(self.status.item())
+        if st:
+            raise RuntimeError(f'halo exchange timed out waiting for rank {st - 1}')
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for ptrs in self.opened.values():
+            for q in ptrs:
+                self.lib.nn_p2p_close_handle(q)
+        for q in self.local:
+            self.lib.nn_p2p_free(q)
+        self.opened, self.local = {}, []
+
+
 class DomainDecomposition:
     """Energy / forces / stress of ONE periodic box across the ranks of a process group.
 
@@ -165,10 +263,13 @@ class DomainDecomposition:
     -> CustomOutputSet with energy [1], gradient_force [N,3] (complete on every rank), stress, virial.
     """
 
-    def __init__(self, model, group=None, grid=None, skin=1.0):
+    def __init__(self, model, group=None, grid=None, skin=1.0, transport='p2p'):
         """skin (A): the brick/ghost plan is kept while no atom has moved more than skin/2 since it was
-        made (the ghost shell is cutoff + skin thick); the neighbour list itself is rebuilt every call."""
+        made (the ghost shell is cutoff + skin thick); the neighbour list itself is rebuilt every call.
+        transport: 'p2p' = pack kernel storing into peer memory over NVLink (csrc/p2p.cu), 'nccl' =
+        pack kernel + all_to_all_single."""
         self.model, self.group, self.grid, self.skin = model, group, grid, float(skin)
+        self.transport = transport
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.plan = None
@@ -192,7 +293,11 @@ class DomainDecomposition:
         self.plan = plan
         self.n_plans += 1
         l2g = torch.from_numpy(plan.local_to_global).to(dev)
-        self._state = dict(l2g=l2g, halo=HaloExchange(plan, dev, self.group), pos_ref=pos.detach().clone(),
+        if self._state is not None and hasattr(self._state['halo'], 'close'):
+            self._state['halo'].close()
+        use_p2p = self.transport == 'p2p' and self.world > 1 and dist.get_backend(self.group) == 'nccl'
+        halo = PeerHaloExchange(plan, dev, self.group) if use_p2p else HaloExchange(plan, dev, self.group)
+        self._state = dict(l2g=l2g, halo=halo, pos_ref=pos.detach().clone(),
                            z_l=z.to(torch.int64)[l2g].contiguous(), n=pos.shape[0],
                            batch_l=torch.zeros(len(plan.local_to_global), dtype=torch.int64, device=dev))
         self._nl = None
@@ -291,6 +396,8 @@ class DomainDecomposition:
             dist.all_reduce(forces, group=self.group)
             dist.all_reduce(red, group=self.group)
         status = nl.check()
+        if hasattr(halo, 'check'):
+            halo.check()
         over = torch.tensor([float(status[L.ST_EDGE_OVERFLOW] != 0)], device=dev)
         if self.world > 1:
             dist.all_reduce(over, op=dist.ReduceOp.MAX, group=self.group)

@@ -30,7 +30,7 @@ def _model(dev, props):
     return m
 
 
-def _dd_worker(rank, world, port, nside, out_path):
+def _dd_worker(rank, world, port, nside, out_path, transport='p2p'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -41,7 +41,7 @@ def _dd_worker(rank, world, port, nside, out_path):
         z, pos, cell, batch = workloads.water_box(nside, seed=3)
         t = lambda a: torch.tensor(a, device=dev)
         model = _model(dev, ['energy', 'gradient_force', 'stress', 'virial'])
-        dd = DomainDecomposition(model)
+        dd = DomainDecomposition(model, transport=transport)
         out = dd(t(z), t(pos), t(cell))
         out2 = dd(t(z), t(pos), t(cell))                 # second call reuses capacities
         assert torch.equal(out.gradient_force, out2.gradient_force)
@@ -57,12 +57,13 @@ def _dd_worker(rank, world, port, nside, out_path):
 
 
 @needs2
+@pytest.mark.parametrize('transport', ['p2p', 'nccl'])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_domain_decomposition_matches_single_gpu(world, tmp_path):
+def test_domain_decomposition_matches_single_gpu(world, transport, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
     path = str(tmp_path / 'dd.npz')
-    mp.spawn(_dd_worker, args=(world, _free_port(), 8, path), nprocs=world, join=True)
+    mp.spawn(_dd_worker, args=(world, _free_port(), 8, path, transport), nprocs=world, join=True)
     d = np.load(path)
     assert abs(d['e'][0] - d['re'][0]) <= 1e-5 * abs(d['re'][0])
     assert np.abs(d['f'] - d['rf']).max() < 2e-5          # same fp32 kernels, different summation split
