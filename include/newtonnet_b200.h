@@ -86,6 +86,7 @@ typedef struct {
     nn_mat W1; const float* b1;     /* interaction_layers.l.message_nodepart.0 */
     nn_mat W2; const float* b2;     /* interaction_layers.l.message_nodepart.2 */
     const float *We, *Wet;          /* message_edgepart.weight [F, nb] and its transpose [nb, F] */
+    const float *We_img;            /* tensor-core operand image of We (nn_message_prepare_b), or NULL */
     nn_mat U1, U2;                  /* equiv_message1.{0,2}.weight */
     nn_mat V1, V2;                  /* equiv_message2.{0,2}.weight */
     nn_mat Wu;                      /* equiv_update.weight */
@@ -226,10 +227,14 @@ NN_API int nn_halo_pack(const float* src, const int32_t* idx, int32_t n, int32_t
  * sweep) drbf[nb] = d rbf / dx. */
 NN_API int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
                             int32_t cap_pairs, float* rbf, float* drbf, float* unit, float* dist, void* stream);
-/* reverse of the above: G_p = dE/d disp_p from x_bar [P] (= dE/dx) and unit_bar [P,3]. */
-NN_API int nn_edge_geom_bwd(const float* x_bar, const float* unit_bar, const float* unit, const float* dist,
-                            float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs, float* disp_bar,
-                            void* stream);
+/* reverse of the above: G_p = dE/d disp_p from dE/dx and unit_bar [P,3]; dE/dx is given as `n_slots`
+ * partial arrays x_bar[slot * cap_pairs + p] (one or two per layer) that are summed in slot order. */
+NN_API int nn_edge_geom_bwd(const float* x_bar, int32_t n_slots, const float* unit_bar, const float* unit,
+                            const float* dist, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
+                            float* disp_bar, void* stream);
+/* image of message_edgepart.weight [128, 20] for the tensor-core message kernels (2 * 4096 floats). */
+#define NN_WE_IMAGE_FLOATS (2 * 128 * 32)
+NN_API int nn_message_prepare_b(const float* We, float* image, void* stream);
 /* m_p = (We rbf_p) * mn_i * mn_j, models/newtonnet.py:210-211. */
 NN_API int nn_edge_message_fwd(const nn_nbr* nl, const float* rbf, const float* mn, const float* Wet,
                         float* msg, void* stream);

@@ -14,6 +14,7 @@ NN_NB = 20
 NN_MAX_LAYERS = 8
 NN_STATUS_WORDS = 8
 NN_B_IMAGE_FLOATS = 2 * 128 * 128
+NN_WE_IMAGE_FLOATS = 2 * 128 * 32
 ST_EDGE_OVERFLOW, ST_ROW_OVERFLOW, ST_BATCH_UNSORTED, ST_SINGULAR_CELL, ST_N_EDGES, ST_N_PAIRS, ST_N_CELLS = range(7)
 STAGES = ['nbr', 'geom', 'node_gemm', 'pair_gemm', 'message', 'aggregate', 'head', 'bwd_gather', 'bwd_message',
           'bwd_aggregate', 'force', 'other']
@@ -30,7 +31,7 @@ class Mat(C.Structure):
 
 
 class LayerWeights(C.Structure):
-    _fields_ = [('W1', Mat), ('b1', _fp), ('W2', Mat), ('b2', _fp), ('We', _fp), ('Wet', _fp),
+    _fields_ = [('W1', Mat), ('b1', _fp), ('W2', Mat), ('b2', _fp), ('We', _fp), ('Wet', _fp), ('We_img', _fp),
                 ('U1', Mat), ('U2', Mat), ('V1', Mat), ('V2', Mat), ('Wu', Mat)]
 
 
@@ -91,7 +92,8 @@ SYMBOLS = {
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
-    'nn_edge_geom_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
+    'nn_edge_geom_bwd': (C.c_int, [_fp, C.c_int32, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
+    'nn_message_prepare_b': (C.c_int, [_fp, _fp, _fp]),
     'nn_edge_message_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp]),
     'nn_node_aggregate_fwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_equiv_update_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int32, _fp]),

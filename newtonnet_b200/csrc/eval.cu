@@ -17,6 +17,9 @@ int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f
                               float* e2bar, float* ubar, bool first, cudaStream_t s);
 int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
                                const float* Wet, float* mbar_io, float* x_bar, cudaStream_t s);
+int nn_message_fwd_tc(const nn_nbr* nl, const float* rbf, const float* mn, const float* We_img, float* msg, cudaStream_t s);
+int nn_message_bwd_tc(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
+                      const float* We_img, float* mbar_io, float* x_part, cudaStream_t s);
 int nn_node_aggregate_bwd_launch(const nn_nbr* nl, int n_rows, const float* t, const float* mn, const float* e2,
                                  const float* dfb, float* mnbar, float* fbar_new, bool first, cudaStream_t s);
 
@@ -117,7 +120,7 @@ struct EvalWs {
     float *abar, *mnbar, *tmpN;           // [N,F]
     float *fbar, *dfb;                    // [N,3,F]
     float *e2bar, *mbar;                  // [P,F]
-    float *x_bar, *ubar, *G;              // [P] (dE/dx), [P,3], [P,3]
+    float *x_bar, *ubar, *G;              // [2L][P] (dE/dx partial slots), [P,3], [P,3]
     float *vir_atom;                      // [N,9]
     size_t total;
 };
@@ -141,7 +144,7 @@ EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
         w.abar = c.take<float>(NF); w.mnbar = c.take<float>(NF); w.tmpN = c.take<float>(NF);
         w.fbar = c.take<float>(3 * NF); w.dfb = c.take<float>(3 * NF);
         w.e2bar = c.take<float>(PF); w.mbar = c.take<float>(PF);
-        w.x_bar = c.take<float>(P); w.ubar = c.take<float>((size_t)P * 3); w.G = c.take<float>((size_t)P * 3);
+        w.x_bar = c.take<float>((size_t)2 * L * P); w.ubar = c.take<float>((size_t)P * 3); w.G = c.take<float>((size_t)P * 3);
         w.vir_atom = c.take<float>((size_t)N * 9);
     }
     w.total = c.off;
@@ -241,7 +244,11 @@ int run_phase(EvalCtx& c, int phase, int l) {
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
-        { ProfScope ps(NN_STAGE_MESSAGE, s); NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s)); }
+        {
+            ProfScope ps(NN_STAGE_MESSAGE, s);
+            if (g_backend == 1 && lw.We_img) NN_TRY(nn_message_fwd_tc(nl, w.rbf, b.mn, lw.We_img, b.msg, s));
+            else NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s));
+        }
         g.fwd(b.msg, lw.U1, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         g.fwd(b.q1, lw.U2, b.e1, P, c.PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
         if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
@@ -271,7 +278,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         g.bwd(w.mnbar, W.H1, w.abar, No, NN_PRO_NONE, NN_EPI_BIAS);
         NN_TRY(g.rc);
         cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
-        cudaMemsetAsync(w.x_bar, 0, (size_t)P * sizeof(float), s);
+        cudaMemsetAsync(w.x_bar, 0, (size_t)2 * L * P * sizeof(float), s);
         cudaMemsetAsync(w.ubar, 0, (size_t)P * 3 * sizeof(float), s);
         return 0;
     }
@@ -293,7 +300,12 @@ int run_phase(EvalCtx& c, int phase, int l) {
             g.bwd(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
         }
         NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_BWD_MESSAGE, s); NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, w.drbf, lw.Wet, w.mbar, w.x_bar, s)); }
+        {
+            ProfScope ps(NN_STAGE_BWD_MESSAGE, s);
+            float* slot = w.x_bar + (size_t)2 * l * P;      // two partial arrays per layer, summed in k_edge_geom_bwd
+            if (g_backend == 1 && lw.We_img) NN_TRY(nn_message_bwd_tc(nl, w.abar, b.mn, w.rbf, w.drbf, lw.We_img, w.mbar, slot, s));
+            else NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, w.drbf, lw.Wet, w.mbar, slot, s));
+        }
         { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, No, w.mbar, b.mn, b.e2, w.dfb, w.mnbar, w.fbar, first, s)); }
         // abar += ((mnbar @ W2) * silu'(pre)) @ W1
         g.bwd(w.mnbar, lw.W2, w.tmpN, No, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
@@ -301,7 +313,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         return g.rc;
     }
     case NN_PH_FINISH: {     // dE/d disp per pair, forces of owned atoms, partial virial
-        { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
+        { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, 2 * L, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
         ProfScope ps(NN_STAGE_FORCE, s);
         NN_TRY(nn_force_virial_rows(nl, No, w.G, c.a->forces, c.a->want_virial ? c.a->virial : nullptr,
                                     c.a->want_virial ? c.a->stress : nullptr, w.vir_atom, s));

@@ -63,7 +63,7 @@ __global__ void k_edge_geom_fwd(const float* __restrict__ disp, const float* __r
 
 // G_p = dE/d disp_p = (xbar / rc) u + (ubar - <ubar,u> u) / d, with xbar = dE/dx accumulated by the
 // reverse message kernels (xbar_p = sum_layers <y_p, We drbf_p>).
-__global__ void k_edge_geom_bwd(const float* __restrict__ x_bar, const float* __restrict__ unit_bar,
+__global__ void k_edge_geom_bwd(const float* __restrict__ x_bar, int n_slots, const float* __restrict__ unit_bar,
                                 const float* __restrict__ unit, const float* __restrict__ dist, float cutoff,
                                 const int* __restrict__ n_dev, int cap, float* __restrict__ disp_bar) {
     const int P = dev_count(n_dev, cap);
@@ -72,7 +72,9 @@ __global__ void k_edge_geom_bwd(const float* __restrict__ x_bar, const float* __
         float3 u = make_float3(unit[3 * p], unit[3 * p + 1], unit[3 * p + 2]);
         float3 ub = make_float3(unit_bar[3 * p], unit_bar[3 * p + 1], unit_bar[3 * p + 2]);
         float dot = ub.x * u.x + ub.y * u.y + ub.z * u.z;
-        float a = x_bar[p] / cutoff, invd = 1.0f / d;
+        float xb = 0.f;
+        for (int sl = 0; sl < n_slots; ++sl) xb += x_bar[(size_t)sl * cap + p];     // fixed order
+        float a = xb / cutoff, invd = 1.0f / d;
         disp_bar[3 * p] = fmaf(a, u.x, (ub.x - dot * u.x) * invd);
         disp_bar[3 * p + 1] = fmaf(a, u.y, (ub.y - dot * u.y) * invd);
         disp_bar[3 * p + 2] = fmaf(a, u.z, (ub.z - dot * u.z) * invd);
@@ -368,7 +370,7 @@ k_pair_bwd_message(const int* __restrict__ pair_ptr, const int* __restrict__ pai
                     w = ld4(s_wet + (4 * q + 3) * kF + 4 * lane); me = f4_fma(rv.w, w, me); dme = f4_fma(dv.w, w, dme);
                 }
                 const float xs = warp_sum(f4_dot(y, dme));
-                if (lane == 0) x_bar[c0 + t] += xs;
+                if (lane == 0) x_bar[c0 + t] = xs;                 // this layer's slot (summed in k_edge_geom_bwd)
                 st4(mbar_io + po, f4_mul(mt, me));
             }
             __syncwarp();
@@ -549,12 +551,12 @@ extern "C" int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float
     return 0;
 }
 
-extern "C" int nn_edge_geom_bwd(const float* x_bar, const float* unit_bar, const float* unit, const float* dist,
-                                float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs, float* disp_bar,
-                                void* stream) {
+extern "C" int nn_edge_geom_bwd(const float* x_bar, int32_t n_slots, const float* unit_bar, const float* unit,
+                                const float* dist, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
+                                float* disp_bar, void* stream) {
     if (cap_pairs <= 0) return 0;
     int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
-    k_edge_geom_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(x_bar, unit_bar, unit, dist, cutoff, n_pairs_dev, cap_pairs,
+    k_edge_geom_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(x_bar, n_slots, unit_bar, unit, dist, cutoff, n_pairs_dev, cap_pairs,
                                                            disp_bar); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_bwd");
     return 0;

@@ -78,6 +78,10 @@ class WeightPack:
             mat(lw.W2, state[k + 'message_nodepart.2.weight'])
             lw.b2 = f32(state[k + 'message_nodepart.2.bias']).data_ptr()
             lw.We, lw.Wet = both(state[k + 'message_edgepart.weight'])
+            we_img = torch.empty(L.NN_WE_IMAGE_FLOATS, dtype=torch.float32, device=dev)
+            self.keep.append(we_img)
+            L.check(lib.nn_message_prepare_b(lw.We, we_img.data_ptr(), stream), 'nn_message_prepare_b')
+            lw.We_img = we_img.data_ptr()
             mat(lw.U1, state[k + 'equiv_message1.0.weight'])
             mat(lw.U2, state[k + 'equiv_message1.2.weight'])
             mat(lw.V1, state[k + 'equiv_message2.0.weight'])

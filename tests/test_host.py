@@ -24,8 +24,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     # struct layouts agree with the header (sizes computed independently with the C compiler rules)
     import ctypes as C
     assert C.sizeof(_lib.Mat) == 4 * 8
-    assert C.sizeof(_lib.LayerWeights) == 7 * 32 + 4 * 8
-    assert C.sizeof(_lib.Weights) == 8 + 2 * 8 + 8 * (7 * 32 + 4 * 8) + 2 * 32 + 6 * 8
+    assert C.sizeof(_lib.LayerWeights) == 7 * 32 + 5 * 8
+    assert C.sizeof(_lib.Weights) == 8 + 2 * 8 + 8 * (7 * 32 + 5 * 8) + 2 * 32 + 6 * 8
     assert C.sizeof(_lib.Nbr) == 6 * 4 + 13 * 8 + 8
     assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 4 * 4
     assert lib.nn_nbr_workspace_bytes(1000, 4) > 0
