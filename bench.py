@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
-    ap.add_argument('--backend', default=os.environ.get('NN_GEMM_BACKEND', 'auto'), choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--backend', default=os.environ.get('NN_GEMM_BACKEND', 'auto'), choices=['auto', 'simt', 'tc', 'ts'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -210,8 +210,8 @@ def main_b200(args):
     lib = L.load()
     backend = args.backend
     if backend == 'auto':
-        backend = 'tc' if lib.nn_get_gemm_backend() == 1 else 'simt'
-    lib.nn_set_gemm_backend(1 if backend == 'tc' else 0)
+        backend = {0: 'simt', 1: 'tc', 2: 'ts'}[lib.nn_get_gemm_backend()]
+    lib.nn_set_gemm_backend({'simt': 0, 'tc': 1, 'ts': 2}[backend])
 
     K, W = args.steps, max(args.warmup, 3)
     if args.workload == 'c4' and world > 1:
@@ -360,7 +360,7 @@ def main_b200(args):
     roofline = None
     if dominant:
         t = table[dominant]
-        roofline = {'kernel': dominant + ('[tcgen05 3xTF32]' if backend == 'tc' and 'gemm' in dominant else
+        roofline = {'kernel': dominant + ('[tcgen05 3xTF32]' if backend in ('tc', 'ts') and 'gemm' in dominant else
                                           ('[fp32 SIMT]' if 'gemm' in dominant else '')),
                     'bound': t['bound'], 'achieved': t['achieved'], 'peak': t['peak'], 'unit': t['unit'],
                     'frac': t['frac'], 'traffic': None, 'peak_source': pk['source'] + (' sustained bf16' if t['bound'] == 'tensor' else ' copy'),
@@ -382,7 +382,7 @@ def main_b200(args):
         'config': {'workload': f'{args.workload}: {workloads.DESCRIPTION[args.workload]}', 'atoms_per_gpu': N,
                    'systems_per_gpu': B, 'directed_edges_per_gpu': n_edges, 'n_features': 128, 'n_basis': 20,
                    'n_interactions': n_layers, 'cutoff': pack.cutoff, 'heads': props,
-                   'gemm_backend': 'tcgen05 3xTF32' if backend == 'tc' else 'fp32 SIMT',
+                   'gemm_backend': {'simt': 'fp32 SIMT', 'tc': 'tcgen05 3xTF32 (A, B in smem)', 'ts': 'tcgen05 3xTF32 (A in TMEM)'}[backend],
                    'parallelism': f'dp{world} (independent batches, no data-path collective)',
                    'cache': 'per-step working set (pair tensors, %.1f GB) exceeds the 126 MB L2; positions change every step'
                             % (n_layers * 5 * P * 512 / 1e9)},
@@ -443,7 +443,7 @@ def main_c4_decomposed(args, world, rank, local, dev, lib, backend, barrier, max
                                           f'+ all-reduce of forces/energy/virial',
                            'owned_atoms_rank0': dd.plan.n_owned, 'ghost_atoms_rank0': dd.plan.n_ghost, 'plans_built': dd.n_plans,
                            'plan_skin_A': dd.skin,
-                           'gemm_backend': 'tcgen05 3xTF32' if backend == 'tc' else 'fp32 SIMT',
+                           'gemm_backend': {'simt': 'fp32 SIMT', 'tc': 'tcgen05 3xTF32 (A, B in smem)', 'ts': 'tcgen05 3xTF32 (A in TMEM)'}[backend],
                            'note': 'every step rebuilds the neighbour list; the brick/ghost plan (host side) is reused while no '
                                    'atom moved more than skin/2; positions resident on every rank, results complete '
                                    'on every rank'},

@@ -169,7 +169,8 @@ NN_API int nn_gemm128(const nn_gemm_args* a, void* stream);
 /* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo
  * parts, laid out as UMMA K-major 128B-swizzled blocks; `image` holds NN_B_IMAGE_FLOATS floats. */
 NN_API int nn_gemm128_prepare_b(const float* B, float* image, void* stream);
-/* backend for nn_gemm128 and nn_eval: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 tensor cores. */
+/* backend for nn_gemm128 and nn_eval: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 with A and B in shared memory,
+ * 2 = tcgen05 3xTF32 with the A operand in tensor memory (TS mode). */
 NN_API int nn_set_gemm_backend(int backend);
 NN_API int nn_get_gemm_backend(void);
 

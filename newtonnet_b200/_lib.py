@@ -122,9 +122,10 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    # dense contractions: tcgen05 3xTF32 tensor-core kernel by default; NN_GEMM_BACKEND=simt selects the
-    # fp32 SIMT kernel (both are CUDA kernels of this library - there is no non-CUDA path)
-    lib.nn_set_gemm_backend(0 if os.environ.get('NN_GEMM_BACKEND', 'tc') == 'simt' else 1)
+    # dense contractions: tcgen05 3xTF32 kernel with the A operand in tensor memory by default;
+    # NN_GEMM_BACKEND=tc selects the shared-memory-operand variant, =simt the fp32 SIMT kernel (all are
+    # CUDA kernels of this library - there is no non-CUDA path)
+    lib.nn_set_gemm_backend({'simt': 0, 'tc': 1}.get(os.environ.get('NN_GEMM_BACKEND', 'ts'), 2))
     _lib = lib
     return lib
 

@@ -10,6 +10,7 @@
 
 int nn_gemm128_simt_launch(const nn_gemm_args& a, cudaStream_t s);
 int nn_gemm128_tc_launch(const nn_gemm_args& a, cudaStream_t s);
+int nn_gemm128_ts_launch(const nn_gemm_args& a, cudaStream_t s);
 int nn_embed_launch(const int64_t* z, const float* emb, float* a, int N, int* status, cudaStream_t s);
 int nn_energy_head_seed_launch(const float* h2pre, const float* w3, const float* scale, const int64_t* z, int N,
                                float* gh2, cudaStream_t s);
@@ -89,13 +90,14 @@ extern "C" int nn_profile_collect(float* ms_per_stage, int* n_per_stage, int n_s
 
 static int g_backend = 0;
 extern "C" int nn_set_gemm_backend(int backend) {
-    if (backend != 0 && backend != 1) { nn_set_error("unknown gemm backend %d", backend); return -1; }
+    if (backend < 0 || backend > 2) { nn_set_error("unknown gemm backend %d", backend); return -1; }
     g_backend = backend;
     return 0;
 }
 extern "C" int nn_get_gemm_backend(void) { return g_backend; }
 
 int nn_gemm128_launch(const nn_gemm_args& a, cudaStream_t s) {
+    if (g_backend == 2) return nn_gemm128_ts_launch(a, s);
     return g_backend == 1 ? nn_gemm128_tc_launch(a, s) : nn_gemm128_simt_launch(a, s);
 }
 extern "C" int nn_gemm128(const nn_gemm_args* a, void* stream) {
@@ -246,7 +248,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
         {
             ProfScope ps(NN_STAGE_MESSAGE, s);
-            if (g_backend == 1 && lw.We_img) NN_TRY(nn_message_fwd_tc(nl, w.rbf, b.mn, lw.We_img, b.msg, s));
+            if (g_backend >= 1 && lw.We_img) NN_TRY(nn_message_fwd_tc(nl, w.rbf, b.mn, lw.We_img, b.msg, s));
             else NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s));
         }
         g.fwd(b.msg, lw.U1, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
@@ -303,7 +305,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         {
             ProfScope ps(NN_STAGE_BWD_MESSAGE, s);
             float* slot = w.x_bar + (size_t)2 * l * P;      // two partial arrays per layer, summed in k_edge_geom_bwd
-            if (g_backend == 1 && lw.We_img) NN_TRY(nn_message_bwd_tc(nl, w.abar, b.mn, w.rbf, w.drbf, lw.We_img, w.mbar, slot, s));
+            if (g_backend >= 1 && lw.We_img) NN_TRY(nn_message_bwd_tc(nl, w.abar, b.mn, w.rbf, w.drbf, lw.We_img, w.mbar, slot, s));
             else NN_TRY(nn_pair_bwd_message_launch(nl, w.abar, b.mn, w.rbf, w.drbf, lw.Wet, w.mbar, slot, s));
         }
         { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, No, w.mbar, b.mn, b.e2, w.dfb, w.mnbar, w.fbar, first, s)); }

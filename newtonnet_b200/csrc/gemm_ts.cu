@@ -1,23 +1,17 @@
-// Tensor-core backend of nn_gemm128: Y[M,128] = epi(pro(X)[M,128] @ B[128,128]) on the 5th-generation
-// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM), fp32-faithful through a 3xTF32 split:
-//     X @ B  ~=  X_lo @ B_hi + X_hi @ B_lo + X_hi @ B_hi ,   hi = x rounded to tf32 (cvt.rna), lo = x - hi.
-// SURVEY.md section 7 measured single-pass TF32 at 1e-3 eV/A force error (fails the 1e-4 bar) and the
-// 3-pass split at the fp32 noise floor, hence three MMAs per K step.
+// TS-mode variant of the tensor-core contraction (backend 2): the A operand lives in TENSOR MEMORY.
 //
-// Kernel shape (persistent, one CTA per SM, 544 threads):
-//   warps 0-7  producers : LDG.128 rows of X (coalesced 128 B lines) -> prologue (SiLU / row scale) ->
-//                          hi/lo split -> st.shared into the UMMA K-major 128B-swizzled layout; one
-//                          pipeline stage = one 32-wide K block (A_hi + A_lo = 32 KB), 2 stages; four
-//                          more K blocks per thread are in flight in registers.
-//   warp  16   MMA issuer: bulk-copies the prepared operand image of B (hi + lo, 128 KB) into shared
-//                          memory once per CTA (cp.async.bulk + mbarrier), then issues 12 tcgen05.mma
-//                          (M128 N128 K8) per stage from one elected lane; tcgen05.commit releases the
-//                          stage / publishes the accumulator.
-//   warps 8-15 epilogue  : tcgen05.ld the 128x128 fp32 accumulator (TMEM lane = row), apply bias /
-//                          SiLU' / residual epilogues, st.global.v4.  Two accumulator buffers (2 x 128
-//                          TMEM columns) let the epilogue of tile t overlap the MMAs of tile t+1.
-// B stays resident in shared memory for all tiles of the CTA: per tile only X is read and Y written, so
-// the kernel is bound by HBM (1 KB per row) rather than by L2 re-reads of the weights.
+// gemm_tc.cu (SS mode) is bound by the shared-memory port of each SM: per 128-row tile the tensor core
+// re-reads A_hi twice, A_lo, B_hi twice and B_lo from shared memory (384 KB), on top of 128 KB of producer
+// stores and 128 KB of epilogue staging - about 5.1k of the 6.5k cycles a tile takes (throughput scales
+// linearly with the number of CTAs: it is per-SM bound, not HBM bound).  Here the producers write the
+// hi / lo split of X straight into TMEM (tcgen05.st, lane = row), so the MMAs read only B from shared
+// memory (192 KB per tile) and the A stage ring in shared memory disappears:
+//   warps 0-7  producers : coalesced LDG.128 (4 K-blocks of prefetch) -> 32x32 transpose through a 4 KB
+//                          XOR-swizzled staging buffer -> row-owner layout -> prologue -> tf32 hi/lo ->
+//                          tcgen05.st into the K block's TMEM columns (warp = lane quarter x K-block half)
+//   warp  16   MMA issuer: tcgen05.mma kind::tf32 with A from TMEM ([taddr]) and B from the resident image
+//   warps 8-15 epilogue  : unchanged (see gemm_tc.cu)
+// TMEM: columns 0-255 two accumulators, 256-511 one tile of A (4 K blocks x (32 hi + 32 lo) columns).
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -25,16 +19,16 @@ namespace {
 
 using namespace tc;
 constexpr int NKB = 4;                        // K blocks per tile (K = 128)
-constexpr int STAGES = 2;
 constexpr uint32_t B_BYTES = 2 * NKB * BLK_BYTES;     // hi + lo image of B = 128 KB
-constexpr uint32_t A_STAGE_BYTES = 2 * BLK_BYTES;     // A_hi + A_lo block = 32 KB
 constexpr uint32_t BAR_BYTES = 256;
-constexpr uint32_t SMEM_BYTES = 1024 + B_BYTES + STAGES * A_STAGE_BYTES + 8 * STG_BYTES + BAR_BYTES;
+constexpr int PDEPTH = 2;                     // cp.async staging buffers per producer warp (items in flight)
+constexpr uint32_t SMEM_BYTES = 1024 + B_BYTES + (8 * PDEPTH + 8) * STG_BYTES + BAR_BYTES;   // B image + producer / epilogue staging
 constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
 constexpr int MMA_WARP = PRODUCER_WARPS + EPI_WARPS;
 constexpr int PF = 4;                         // producer register prefetch depth in K blocks (one whole tile)
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 1);
-constexpr uint32_t TMEM_COLS = 256;           // two 128-column fp32 accumulators
+constexpr uint32_t TMEM_COLS = 512;           // 2 x 128 accumulator columns + 4 K blocks x 64 columns of A
+constexpr uint32_t A_COL0 = 256;
 
 // Loads are issued raw (so they stay in flight); the prologue is applied when the value is consumed.
 template <int PRO>
@@ -78,17 +72,17 @@ __device__ __forceinline__ float4 epilogue(const nn_gemm_args& a, float4 acc, in
 }
 
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(THREADS, 1) k_gemm128_tc(nn_gemm_args a) {
+__global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
     const uint32_t sB = base;                                             // [hi|lo][kb][16 KB]
-    const uint32_t sA = base + B_BYTES;                                   // [stage][hi|lo][16 KB]
-    const uint32_t sStg = sA + STAGES * A_STAGE_BYTES;                    // [8 epilogue warps][4 KB]
+    const uint32_t sPst = base + B_BYTES;                                 // [8 producer warps][PDEPTH][4 KB]
+    const uint32_t sStg = sPst + 8 * PDEPTH * STG_BYTES;                  // [8 epilogue warps][4 KB]
     const uint32_t sBar = sStg + 8 * STG_BYTES;
     const uint32_t bar_b_full = sBar;                                     // 8 bytes each
-    const uint32_t bar_a_full = sBar + 8;                                 // [STAGES]
-    const uint32_t bar_a_empty = bar_a_full + 8 * STAGES;                 // [STAGES]
-    const uint32_t bar_t_full = bar_a_empty + 8 * STAGES;                 // [2]
+    const uint32_t bar_a_full = sBar + 8;                                 // [NKB] one per K block of the tile in TMEM
+    const uint32_t bar_a_empty = bar_a_full + 8 * NKB;                    // [NKB]
+    const uint32_t bar_t_full = bar_a_empty + 8 * NKB;                    // [2]
     const uint32_t bar_t_empty = bar_t_full + 16;                         // [2]
     const uint32_t tmem_slot = bar_t_empty + 16;                          // 4 bytes
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));           // generic pointer to `base`
@@ -102,7 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_tc(nn_gemm_args a) {
     if (warp == MMA_WARP) {
         if (lane == 0) {
             mbar_init(bar_b_full, 1);
-            for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a_full + 8 * s, PRODUCER_WARPS * 32); mbar_init(bar_a_empty + 8 * s, 1); }
+            for (int s = 0; s < NKB; ++s) { mbar_init(bar_a_full + 8 * s, 4 * 32); mbar_init(bar_a_empty + 8 * s, 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full + 8 * b, 1); mbar_init(bar_t_empty + 8 * b, EPI_WARPS * 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -116,47 +110,74 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_tc(nn_gemm_args a) {
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
     if (warp < PRODUCER_WARPS) {
-        // ===================== producers: X rows -> hi/lo split -> swizzled smem =====================
-        // Work items w = (tile, K block); each thread keeps PF items (PF x 4 LDG.128) in flight in
-        // registers so ~64 KB of reads per SM are outstanding (HBM latency x bandwidth / 148 SMs).
-        const int r4 = lane >> 3, chunk = lane & 7;
+        // ===================== producers: X rows -> transpose -> hi/lo split -> TMEM =====================
+        // warp = (lane quarter q, K-block half h): rows [32q, 32q+32) of K blocks 2h and 2h+1 of every tile.
+        // cp.async (LDGSTS) brings each 32 x 32 block into a swizzled staging buffer in the coalesced
+        // layout with no registers held (PDEPTH blocks = 8 KB per warp, 64 KB per SM in flight); the block
+        // is then read back one ROW per lane, split and stored to the K block's TMEM columns.
+        const int q = warp & 3, h = warp >> 2;
+        const int r4 = lane >> 3, c8 = lane & 7;
+        const uint32_t pst_s = sPst + warp * PDEPTH * STG_BYTES;
+        uint8_t* pst_g = smem_gen + (pst_s - base);
         const int my_tiles = has_work ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const int n_items = my_tiles * NKB;
-        float4 v[PF][4];
-        auto issue = [&](int w, float4 (&dst)[4]) {
-            const int row0 = ((int)blockIdx.x + (w >> 2) * (int)gridDim.x) * TM, kb = w & 3;
+        const int n_items = my_tiles * 2;                 // item w = (tile w >> 1, K block 2h + (w & 1))
+        auto issue = [&](int w) {
+            const int row0 = ((int)blockIdx.x + (w >> 1) * (int)gridDim.x) * TM + q * 32, kb = 2 * h + (w & 1);
+            const uint32_t dst0 = pst_s + (w % PDEPTH) * STG_BYTES;
 #pragma unroll
-            for (int it = 0; it < 4; ++it)
-                dst[it] = load_a<PRO>(a, row0 + warp * 16 + it * 4 + r4, kb * KB + chunk * 4, M);
+            for (int it = 0; it < 8; ++it) {
+                const int row = it * 4 + r4, grow = row0 + row;
+                const uint32_t dst = dst0 + row * 128 + ((c8 ^ (row & 7)) << 4);
+                const float* src = a.X + (size_t)(grow < M ? grow : 0) * 128 + kb * KB + c8 * 4;
+                const uint32_t nbytes = grow < M ? 16u : 0u;          // rows beyond M are zero-filled
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
 #pragma unroll
-        for (int u = 0; u < PF; ++u)
-            if (u < n_items) issue(u, v[u]);
-        uint32_t stage = 0, phase = 0;
-        for (int w0 = 0; w0 < n_items; w0 += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int w = w0 + u;
-                if (w >= n_items) break;
-                const int crow0 = ((int)blockIdx.x + (w >> 2) * (int)gridDim.x) * TM, ckb = w & 3;
-                mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
-                uint8_t* hi = smem_gen + (sA - base) + stage * A_STAGE_BYTES;
-                uint8_t* lo = hi + BLK_BYTES;
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int row = warp * 16 + it * 4 + r4;
-                    const uint32_t off = swz_offset_bytes(row, chunk);
-                    const float4 x = apply_prologue<PRO>(a, v[u][it], crow0 + row, ckb * KB + chunk * 4, M);
-                    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-                    *reinterpret_cast<float4*>(hi + off) = h;
-                    *reinterpret_cast<float4*>(lo + off) = f4_sub(x, h);
-                }
-                fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(bar_a_full + 8 * stage);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                if (w + PF < n_items) issue(w + PF, v[u]);
-            }
+        for (int u = 0; u < PDEPTH; ++u) {
+            if (u < n_items) issue(u);
+            else asm volatile("cp.async.commit_group;" ::: "memory");    // keep the group count uniform
         }
+        for (int w = 0; w < n_items; ++w) {
+            const int t_local = w >> 1, kb = 2 * h + (w & 1);
+            const int grow = ((int)blockIdx.x + t_local * (int)gridDim.x) * TM + q * 32 + lane;   // this lane's row
+            asm volatile("cp.async.wait_group %0;" ::"n"(PDEPTH - 1) : "memory");
+            __syncwarp();
+            const uint8_t* blk = pst_g + (w % PDEPTH) * STG_BYTES;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + kb * 64;
+            bool waited = false;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                  // 16 K values at a time: 32 live registers
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = hf * 4 + j;
+                    float4 x = *reinterpret_cast<const float4*>(blk + lane * 128 + ((ch ^ (lane & 7)) << 4));
+                    if (PRO == NN_PRO_ROWSCALE3 && grow < M) x = f4_mul(x, ld4(a.aux2 + (size_t)(grow / 3) * 128 + kb * KB + 4 * ch));
+                    x = apply_prologue<PRO>(a, x, grow, kb * KB + 4 * ch, M);
+                    const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    hi[4 * j] = __float_as_uint(hh.x); hi[4 * j + 1] = __float_as_uint(hh.y);
+                    hi[4 * j + 2] = __float_as_uint(hh.z); hi[4 * j + 3] = __float_as_uint(hh.w);
+                    lo[4 * j] = __float_as_uint(x.x - hh.x); lo[4 * j + 1] = __float_as_uint(x.y - hh.y);
+                    lo[4 * j + 2] = __float_as_uint(x.z - hh.z); lo[4 * j + 3] = __float_as_uint(x.w - hh.w);
+                }
+                if (!waited) {    // the MMAs of the previous tile that read this K block's columns must have retired
+                    mbar_wait(bar_a_empty + 8 * kb, (t_local & 1) ^ 1);
+                    tc_fence_after();
+                    waited = true;
+                }
+                tmem_st16(taddr + hf * 16, hi);
+                tmem_st16(taddr + 32 + hf * 16, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * kb);
+            __syncwarp();                                     // every lane has read the staging block
+            if (w + PDEPTH < n_items) issue(w + PDEPTH);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == MMA_WARP) {
         // ===================== B load + MMA issue (one elected lane) =====================
         if (lane == 0 && has_work) {
@@ -164,27 +185,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_tc(nn_gemm_args a) {
             for (int c = 0; c < (int)(B_BYTES / BLK_BYTES); ++c)
                 bulk_g2s(sB + c * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + (size_t)c * BLK_BYTES, BLK_BYTES, bar_b_full);
             mbar_wait(bar_b_full, 0);
-            uint32_t stage = 0, phase = 0, it = 0;
+            uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
                 mbar_wait(bar_t_empty + 8 * buf, acc_phase ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 128;
                 for (int kb = 0; kb < NKB; ++kb) {
-                    mbar_wait(bar_a_full + 8 * stage, phase);
+                    mbar_wait(bar_a_full + 8 * kb, it & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = sA + stage * A_STAGE_BYTES, a_lo = a_hi + BLK_BYTES;
+                    const uint32_t a_hi = tmem_base + A_COL0 + kb * 64, a_lo = a_hi + 32;
                     const uint32_t b_hi = sB + kb * BLK_BYTES, b_lo = b_hi + NKB * BLK_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < KB / 8; ++ks) {                  // UMMA_K = 8 tf32 = 32 bytes
-                        const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
+                    for (int ks = 0; ks < KB / 8; ++ks) {                  // UMMA_K = 8 tf32 = 8 TMEM columns / 32 bytes
                         const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
-                        umma_tf32(d_tmem, dal, dbh, (kb | ks) != 0);       // small terms first
-                        umma_tf32(d_tmem, dah, dbl, 1);
-                        umma_tf32(d_tmem, dah, dbh, 1);
+                        umma_tf32_ts(d_tmem, a_lo + ks * 8, dbh, (kb | ks) != 0);   // small terms first
+                        umma_tf32_ts(d_tmem, a_hi + ks * 8, dbl, 1);
+                        umma_tf32_ts(d_tmem, a_hi + ks * 8, dbh, 1);
                     }
-                    umma_commit(bar_a_empty + 8 * stage);                  // stage reusable once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(bar_a_empty + 8 * kb);                     // K block's TMEM columns reusable
                 }
                 umma_commit(bar_t_full + 8 * buf);                         // accumulator complete
             }
@@ -273,27 +292,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_tc(nn_gemm_args a) {
     }
 }
 
-// B [K=128][N=128] row-major  ->  image[hi|lo][kb][n][swizzled 16 B chunks] of B^T (operand rows = n)
-__global__ void k_prepare_b(const float* __restrict__ B, float* __restrict__ img) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 128 * 128) return;
-    int n = t >> 7, k = t & 127;
-    float x = B[(size_t)k * 128 + n];
-    float hi = tf32_hi(x);
-    int kb = k >> 5, chunk = (k & 31) >> 2, e = k & 3;
-    uint32_t off = (uint32_t)kb * BLK_BYTES + swz_offset_bytes(n, chunk) + e * 4;
-    img[off / 4] = hi;
-    img[(NKB * BLK_BYTES + off) / 4] = x - hi;
-}
-
 int g_num_sms = 0;
 bool g_attr_set[4][5] = {};
 
 template <int PRO, int EPI>
 int launch(const nn_gemm_args& a, cudaStream_t s) {
     if (!g_attr_set[PRO][EPI]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm128_tc<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e != cudaSuccess) { nn_set_error("nn_gemm128(tc): cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
+        cudaError_t e = cudaFuncSetAttribute(k_gemm128_ts<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { nn_set_error("nn_gemm128(ts): cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
         g_attr_set[PRO][EPI] = true;
     }
     if (g_num_sms == 0) {
@@ -303,21 +309,13 @@ int launch(const nn_gemm_args& a, cudaStream_t s) {
     }
     int tiles = nn_ceil_div(a.m, TM);
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    if (const char* e = getenv("NN_TC_GRID")) { int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // experiments only
-    k_gemm128_tc<PRO, EPI><<<grid, THREADS, SMEM_BYTES, s>>>(a); NN_LAUNCHED(1);
+    k_gemm128_ts<PRO, EPI><<<grid, THREADS, SMEM_BYTES, s>>>(a); NN_LAUNCHED(1);
     return 0;
 }
 
 }  // namespace
 
-extern "C" int nn_gemm128_prepare_b(const float* B, float* image, void* stream) {
-    NN_REQUIRE(B && image, "null pointer");
-    k_prepare_b<<<128 * 128 / 256, 256, 0, (cudaStream_t)stream>>>(B, image); NN_LAUNCHED(1);
-    NN_CHECK_LAUNCH("nn_gemm128_prepare_b");
-    return 0;
-}
-
-int nn_gemm128_tc_launch(const nn_gemm_args& a, cudaStream_t s) {
+int nn_gemm128_ts_launch(const nn_gemm_args& a, cudaStream_t s) {
     if (a.m <= 0) return 0;
     NN_REQUIRE(a.B_img != nullptr, "tensor-core backend needs B_img (nn_gemm128_prepare_b)");
     int rc = -1;
@@ -334,6 +332,6 @@ int nn_gemm128_tc_launch(const nn_gemm_args& a, cudaStream_t s) {
     return -1;
 done:
     if (rc) return rc;
-    NN_CHECK_LAUNCH("nn_gemm128(tc)");
+    NN_CHECK_LAUNCH("nn_gemm128(ts)");
     return 0;
 }

@@ -24,17 +24,17 @@ def dev():
     return torch.device('cuda:0')
 
 
-@pytest.fixture(scope='module', params=[0, 1], ids=['simt', 'tcgen05'])
+@pytest.fixture(scope='module', params=[0, 1, 2], ids=['simt', 'tcgen05', 'tcgen05_ts'])
 def backend(request):
     from newtonnet_b200 import _lib
     lib = _lib.load()
-    if request.param == 1:
+    if request.param >= 1:
         probe = torch.zeros(128, 128, device=dev())
         if not _tc_available(lib, probe):
             pytest.skip('tcgen05 backend not built')
     lib.nn_set_gemm_backend(request.param)
     yield request.param
-    lib.nn_set_gemm_backend(1)
+    lib.nn_set_gemm_backend(2)
 
 
 def _tc_available(lib, probe):

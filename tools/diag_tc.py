@@ -29,8 +29,9 @@ def gemm(X, B, backend):
 k = torch.arange(128, device=dev, dtype=torch.float32)
 B = k[:, None] * 128 + k[None, :]          # B[k][n] = 128 k + n  (exact in hi + lo)
 X = torch.eye(128, device=dev)
-Y = gemm(X, B, 1)
-print('identity @ B: max err', float((Y - B).abs().max()))
+for be_ in (1, 2):
+    Y = gemm(X, B, be_)
+    print(f'backend {be_} identity @ B: max err', float((Y - B).abs().max()))
 if float((Y - B).abs().max()) > 0.5:
     print('Y[0,:8]  ', Y[0, :8].tolist())
     print('Y[1,:8]  ', Y[1, :8].tolist())
@@ -45,7 +46,7 @@ for M in (128, 1000, 148 * 128 * 2 + 5):
     g = torch.Generator().manual_seed(M)
     X = torch.randn(M, 128, generator=g).to(dev); B = (torch.randn(128, 128, generator=g) / 11.3).to(dev)
     ref = X.double() @ B.double()
-    for be, name in ((0, 'simt'), (1, 'tc  ')):
+    for be, name in ((0, 'simt'), (1, 'tc  '), (2, 'ts  ')):
         Y = gemm(X, B, be)
         err = (Y.double() - ref).abs().max().item()
         print(f'M={M:6d} {name}: max abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})')
@@ -53,14 +54,15 @@ for M in (128, 1000, 148 * 128 * 2 + 5):
 M = 1_800_000
 X = torch.randn(M, 128, device=dev); B = torch.randn(128, 128, device=dev) / 11.3
 AUX = torch.randn(M, 128, device=dev)
-for be, name, pro, epi in ((0, 'simt plain', 0, 0), (1, 'tc   plain', 0, 0), (1, 'tc   silu-in', 1, 0), (1, 'tc   dsilu-out', 0, 1),
-                           (1, 'tc   add-out', 0, 2), (0, 'simt dsilu-out', 0, 1)):
+for be, name, pro, epi in ((1, 'tc   plain', 0, 0), (2, 'ts   plain', 0, 0), (1, 'tc   silu-save', 3, 0), (2, 'ts   silu-save', 3, 0),
+                           (1, 'tc   mul-out', 0, 4), (2, 'ts   mul-out', 0, 4), (1, 'tc   add-out', 0, 2), (2, 'ts   add-out', 0, 2)):
     gemm(X[:1024], B, be)
     lib.nn_set_gemm_backend(be)
     a = L.GemmArgs(); Y = torch.empty_like(X); img = torch.empty(L.NN_B_IMAGE_FLOATS, device=dev)
     lib.nn_gemm128_prepare_b(B.data_ptr(), img.data_ptr(), s)
     a.X, a.B, a.B_img, a.Y, a.m = X.data_ptr(), B.data_ptr(), img.data_ptr(), Y.data_ptr(), M
     a.prologue, a.epilogue, a.aux1 = pro, epi, AUX.data_ptr()
+    SAVE = torch.empty_like(X); a.aux_out = SAVE.data_ptr()
     for _ in range(3):
         lib.nn_gemm128(C.byref(a), s)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
