@@ -368,12 +368,15 @@ def main_b200(args):
         if dominant == 'pair_gemm':   # the same launches as fp32-equivalent FLOP/s (one 2*128*128 product per row)
             roofline['tflops_fp32_equivalent'] = 2.0 * P * F * F * t['launches'] / K / (t['ms_total'] * 1e-3 / K) * 1e-12
             roofline['tensor_pipe_passes'] = 3
-        if dominant == 'pair_gemm':   # ncu --set full, plain variant, per launch (profiles/r1_ncu_full_summary.txt)
-            roofline['traffic'] = None
+        if dominant == 'pair_gemm' and args.workload == 'c2':
+            # ncu --set full on this workload (profiles/ncu_r1/k_gemm128_ts.raw.csv): the multiply-epilogue variant
+            # moves dram read 1.847 GB + write 0.887 GB per launch for 1536 B x 1,802,624 rows = 2.769 GB algorithmic
+            roofline['traffic'] = 2.734e9
+            roofline['traffic_note'] = 'bytes per launch of the <NONE,MUL> variant (ncu dram__bytes_read+write); algorithmic 2.769e9'
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_base, _, _, _ = run_oracle_timed(args.workload, steps=3, warmup=1, budget_s=30.0)
+        cpu_base, _, _, _ = run_oracle_timed(args.workload, steps=40, warmup=1, budget_s=15.0)   # ~15 s of CPU work
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
