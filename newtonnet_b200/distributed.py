@@ -388,24 +388,31 @@ class DomainDecomposition:
             phase(L.PH_BWD_PAIR, l)
         phase(L.PH_FINISH)
 
-        # ---- complete the sums across ranks
-        forces = torch.zeros(N, 3, **f32)
-        forces[l2g[:n_owned]] = forces_l[:n_owned]
-        red = torch.cat([energy.double(), virial.double().reshape(-1), stress.double().reshape(-1)])
+        # ---- complete the sums across ranks: ONE all-reduce of [forces | energy, virial, stress (hi, lo) | flags]
+        status_dev = nl.status.to(torch.float32)
+        small = torch.cat([energy.double(), virial.double().reshape(-1), stress.double().reshape(-1)])
+        hi = small.float()
+        lo = (small - hi.double()).float()                       # fp64 partial sums travel as two fp32 parts
+        over_flag = (status_dev[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).float()
+        buf = torch.zeros(3 * N + 2 * 19 + 1, **f32)
+        buf[:3 * N].view(N, 3)[l2g[:n_owned]] = forces_l[:n_owned]
+        buf[3 * N:3 * N + 19] = hi
+        buf[3 * N + 19:3 * N + 38] = lo
+        buf[3 * N + 38:] = over_flag
         if self.world > 1:
-            dist.all_reduce(forces, group=self.group)
-            dist.all_reduce(red, group=self.group)
+            dist.all_reduce(buf, group=self.group)
+        forces = buf[:3 * N].view(N, 3)
+        tail = buf[3 * N:].cpu()                                  # the one host synchronisation of the step
+        red = tail[:19].double() + tail[19:38].double()
         status = nl.check()
         if hasattr(halo, 'check'):
             halo.check()
-        over = torch.tensor([float(status[L.ST_EDGE_OVERFLOW] != 0)], device=dev)
-        if self.world > 1:
-            dist.all_reduce(over, op=dist.ReduceOp.MAX, group=self.group)
-        if over.item() > 0:      # some rank's list outgrew its capacity: resize everywhere and repeat
+        if float(tail[38]) > 0:      # some rank's list outgrew its capacity: resize everywhere and repeat
             self._nl = None
             return self.__call__(z, pos, cell, want_virial)
         dt = pos.dtype
         out = CustomOutputSet(z=z, pos=pos, cell=cell, batch=torch.zeros(N, dtype=torch.int64, device=dev))
+        red = red.to(dev)
         out.energy = red[:1].to(dt)
         out.gradient_force = forces.to(dt)
         out.virial = red[1:10].reshape(1, 3, 3).to(dt)

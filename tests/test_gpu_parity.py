@@ -280,6 +280,35 @@ def test_capacity_regrow_and_reuse():
     assert np.abs(o2.gradient_force.cpu().double().numpy() - ref['forces']).max() < F_ATOL
 
 
+def test_other_hyperparameters_against_oracle():
+    """2 interaction layers, cutoff 4.2 A, fp64 model and inputs (cast at the boundary), an empty system in the
+    batch - against the oracle directly (no golden fixture needed: the oracle is pinned to the reference)."""
+    from newtonnet_b200.models import NewtonNet
+    from oracle import newtonnet_oracle as O
+    torch.manual_seed(5)
+    model = NewtonNet(cutoff=4.2, n_interactions=2, output_properties=['energy', 'gradient_force', 'stress']).double()
+    with torch.no_grad():
+        model.scalers[0].scale.weight.uniform_(0.5, 1.5); model.scalers[0].shift.weight.normal_()
+    sd = {k: v.detach().float().numpy() for k, v in model.state_dict().items()}   # fp32-rounded weights for both sides
+    model.load_state_dict({k: torch.tensor(v).double() for k, v in sd.items()})
+    model = model.to(dev()); model.eval()
+    z1, p1, c1, b1 = O.water_box(4, seed=8)
+    z2, p2, c2, b2 = O.water_box(5, seed=9)
+    z = np.concatenate([z1, z2]); pos = np.concatenate([p1, p2])
+    cell = np.concatenate([c1, np.eye(3, dtype=np.float32)[None] * 20.0, c2])          # system 1 has no atoms
+    batch = np.concatenate([b1, b2 + 2])
+    out = model(torch.tensor(z, device=dev()), torch.tensor(pos, device=dev()).double(),
+                torch.tensor(cell, device=dev()).double(), torch.tensor(batch, device=dev()))
+    assert out.energy.dtype == torch.float64 and out.energy.shape == (3,)
+    ref = O.forward(sd, z, pos, cell, batch, dtype=torch.float64, stress=True, cutoff=4.2)
+    assert float(out.energy[1]) == 0.0 and ref['energy'][1] == 0.0
+    np.testing.assert_allclose(out.energy.cpu().numpy(), ref['energy'], rtol=E_RTOL, atol=1e-4)
+    assert np.abs(out.gradient_force.cpu().numpy() - ref['forces']).max() < F_ATOL
+    assert np.array_equal(out.edge_index.cpu().numpy(), ref['edge_index'])
+    s_ref = ref['stress'][[0, 2]]; s_got = out.stress.cpu().numpy()[[0, 2]]
+    assert np.abs(s_got - s_ref).max() < 1e-4 * np.abs(s_ref).max()
+
+
 def test_head_order_and_energy_only():
     d, w = load_case('aspirin1')
     out = run_model(make_model(w, ['energy']), d)
