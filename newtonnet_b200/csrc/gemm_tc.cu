@@ -303,7 +303,6 @@ int launch(const nn_gemm_args& a, cudaStream_t s) {
     }
     int tiles = nn_ceil_div(a.m, TM);
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    if (const char* e = getenv("NN_TC_GRID")) { int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // experiments only
     k_gemm128_tc<PRO, EPI><<<grid, THREADS, SMEM_BYTES, s>>>(a); NN_LAUNCHED(1);
     return 0;
 }

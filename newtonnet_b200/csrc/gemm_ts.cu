@@ -25,7 +25,6 @@ constexpr int PDEPTH = 2;                     // cp.async staging buffers per pr
 constexpr uint32_t SMEM_BYTES = 1024 + B_BYTES + (8 * PDEPTH + 8) * STG_BYTES + BAR_BYTES;   // B image + producer / epilogue staging
 constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
 constexpr int MMA_WARP = PRODUCER_WARPS + EPI_WARPS;
-constexpr int PF = 4;                         // producer register prefetch depth in K blocks (one whole tile)
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 1);
 constexpr uint32_t TMEM_COLS = 512;           // 2 x 128 accumulator columns + 4 K blocks x 64 columns of A
 constexpr uint32_t A_COL0 = 256;

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; all arithmetic happens in
 libnewtonnet_b200.so (include/newtonnet_b200.h).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -138,6 +139,7 @@ class NeighborList:
         s.workspace, s.workspace_bytes = self.workspace.data_ptr(), ws_bytes
         self.struct = s
         self.n_edges = None   # known on the host after `check()`
+        self.generation = 0   # bumped every time the list is rebuilt in place
 
     def rebind(self, pos, cell, batch):
         """Point the list at new input tensors of the same shapes (next MD step)."""
@@ -162,8 +164,11 @@ class NeighborList:
         self.n_edges = st[L.ST_N_EDGES]
         return st
 
-    def edge_index(self):
+    def edge_index(self, generation=None):
         """[2,E] int64, reference order (i-major, j ascending)."""
+        if generation is not None and generation != self.generation:
+            raise RuntimeError('edge_index of an earlier forward() was requested after the neighbour list had been '
+                               'rebuilt in place by a later call; read it before the next forward()')
         if self.n_edges is None:
             self.check()
         out = torch.empty(2, self.n_edges, dtype=torch.int64, device=self.pos.device)
@@ -187,6 +192,9 @@ class Engine:
         self._nl = None
         self._ws = None
         self.launches = 0
+        self.use_cuda_graphs = os.environ.get('NN_CUDA_GRAPHS', '1') != '0'
+        self._graphs = {}
+        self._last_key = None
 
     # ------------------------------------------------------------------ neighbour list
     def neighbor_list(self, pos, cell, batch, cutoff):
@@ -202,6 +210,7 @@ class Engine:
         if reuse:
             nl.rebind(pos, cell, batch)
             nl.n_edges = None
+            nl.generation += 1
             L.check(self.lib.nn_nbr_count(C.byref(nl.struct), cutoff, s), 'nn_nbr_count')
             L.check(self.lib.nn_nbr_fill(C.byref(nl.struct), cutoff, s), 'nn_nbr_fill')
             return nl   # overflow (if any) is detected by the caller's status check -> `grow`
@@ -264,7 +273,28 @@ class Engine:
         return out
 
     def energy_forces(self, weights, z, pos, cell, batch, want_forces=True, want_virial=False, want_nodes=False):
-        """Neighbour list + evaluation + status check, regrowing capacities when needed."""
+        """Neighbour list + evaluation + status check, regrowing capacities when needed.  From the second
+        call with the same shapes on, the whole step (neighbour rebuild + ~80 kernels) is replayed as one
+        CUDA graph."""
+        if self.use_cuda_graphs:
+            key = (pos.shape[0], cell.reshape(-1, 9).shape[0], bool(want_forces), bool(want_virial), bool(want_nodes),
+                   id(weights), str(pos.device))
+            g = self._graphs.get(key)
+            if g is not None:
+                out = g.replay(z, pos, cell, batch)
+                if out is not None:
+                    return out
+                del self._graphs[key]                         # capacity overflow: fall through, recapture later
+            elif self._last_key == key and self._nl is not None and self._nl.n_atoms == pos.shape[0]:
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = GraphedStep(self, weights, z, pos, cell, batch, want_forces, want_virial, want_nodes,
+                                                self._nl.cap_edges)
+                out = self._graphs[key].replay(z, pos, cell, batch)
+                if out is not None:
+                    return out
+                del self._graphs[key]
+            self._last_key = key
         nl = self.neighbor_list(pos, cell, batch, weights.cutoff)
         out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes)
         st = nl.check()
@@ -275,6 +305,73 @@ class Engine:
             if st[L.ST_EDGE_OVERFLOW]:
                 raise RuntimeError('neighbour list capacity overflow after regrow')
         out['_nl'] = nl
+        return out
+
+
+class GraphedStep:
+    """One evaluation (neighbour rebuild + nn_eval) captured as a CUDA graph over static buffers."""
+
+    def __init__(self, engine, weights, z, pos, cell, batch, want_forces, want_virial, want_nodes, cap_edges):
+        dev = pos.device
+        self.engine, self.weights = engine, weights
+        self.z = torch.empty(z.shape, dtype=torch.int64, device=dev)
+        self.pos = torch.empty(pos.shape, dtype=torch.float32, device=dev)
+        self.cell = torch.empty(cell.reshape(-1, 3, 3).shape, dtype=torch.float32, device=dev)
+        self.batch = torch.empty(batch.shape, dtype=torch.int64, device=dev)
+        self._copy_in(z, pos, cell, batch)
+        self.nl = NeighborList(engine, self.pos, self.cell, self.batch, cap_edges=cap_edges)
+        N, B = self.nl.n_atoms, self.nl.n_systems
+        f32 = dict(dtype=torch.float32, device=dev)
+        bwd = want_forces or want_virial
+        self.out = {'energy': torch.empty(B, **f32)}
+        if bwd:
+            self.out['forces'] = torch.empty(N, 3, **f32)
+        if want_virial:
+            self.out['virial'] = torch.empty(B, 3, 3, **f32)
+            self.out['stress'] = torch.empty(B, 3, 3, **f32)
+        if want_nodes:
+            self.out['atom_node'] = torch.empty(N, L.NN_F, **f32)
+            self.out['force_node'] = torch.empty(N, 3, L.NN_F, **f32)
+        nbytes = engine.lib.nn_eval_workspace_bytes(N, B, self.nl.cap_pairs, weights.n_layers, int(bwd))
+        self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        a = L.EvalArgs()
+        a.nbr, a.w, a.z = C.pointer(self.nl.struct), C.pointer(weights.struct), self.z.data_ptr()
+        a.want_forces, a.want_virial = int(bwd), int(want_virial)
+        a.energy = self.out['energy'].data_ptr()
+        a.forces, a.virial, a.stress = L.ptr(self.out.get('forces')), L.ptr(self.out.get('virial')), L.ptr(self.out.get('stress'))
+        a.atom_node, a.force_node = L.ptr(self.out.get('atom_node')), L.ptr(self.out.get('force_node'))
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        self.args = a
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+
+    def _launch(self):
+        lib, s = self.engine.lib, _stream()
+        L.check(lib.nn_nbr_count(C.byref(self.nl.struct), self.weights.cutoff, s), 'nn_nbr_count')
+        L.check(lib.nn_nbr_fill(C.byref(self.nl.struct), self.weights.cutoff, s), 'nn_nbr_fill')
+        L.check(lib.nn_eval(C.byref(self.args), s), 'nn_eval')
+
+    def _copy_in(self, z, pos, cell, batch):
+        self.z.copy_(z, non_blocking=True)
+        self.pos.copy_(pos.detach(), non_blocking=True)
+        self.cell.copy_(cell.detach().reshape(-1, 3, 3), non_blocking=True)
+        self.batch.copy_(batch, non_blocking=True)
+
+    def replay(self, z, pos, cell, batch):
+        """Returns the result dict, or None when the captured capacities overflowed (caller regrows)."""
+        for t, n in ((pos, 'pos'), (cell, 'cell'), (batch, 'batch'), (z, 'z')):
+            _require_cuda(t, n)
+        self._copy_in(z, pos, cell, batch)
+        self.nl.n_edges = None
+        self.nl.generation += 1
+        self.graph.replay()
+        out = {k: v.clone() for k, v in self.out.items()}
+        st = self.nl.check()
+        if st[L.ST_EDGE_OVERFLOW]:
+            return None
+        out['_nl'] = self.nl
         return out
 
 

@@ -111,7 +111,8 @@ class NewtonNet(nn.Module):
         dt = pos.dtype
         nl = res['_nl']
         displacement = torch.eye(3, dtype=dt, device=pos.device).repeat(cell.shape[0], 1, 1)
-        outputs = CustomOutputSet(_lazy={'edge_index': nl.edge_index}, z=z, pos=pos, cell=cell,
+        generation = nl.generation
+        outputs = CustomOutputSet(_lazy={'edge_index': lambda: nl.edge_index(generation)}, z=z, pos=pos, cell=cell,
                                   displacement=displacement, batch=batch)
         if self.return_node_features:
             outputs.atom_node = res['atom_node'].to(dt)
