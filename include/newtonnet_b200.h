@@ -90,6 +90,7 @@ typedef struct {
     nn_mat U1, U2;                  /* equiv_message1.{0,2}.weight */
     nn_mat V1, V2;                  /* equiv_message2.{0,2}.weight */
     nn_mat Wu;                      /* equiv_update.weight */
+    const float *ln_gamma, *ln_beta; /* layer_norm.{weight,bias} [F] (layer_norm=True, models/newtonnet.py:202-205) or NULL */
 } nn_layer_weights;
 
 typedef struct {
@@ -102,6 +103,11 @@ typedef struct {
     nn_mat H2; const float* hb2;    /* output_layers.k.layers.2 */
     const float *w3, *hb3;          /* output_layers.k.layers.4  ([1,F], [1]) */
     const float *scale, *shift;     /* scalers.k.{scale,shift}.weight [119] */
+    /* optional direct_force head (models/output.py:115-132): layers.{0,2,4} 128->128 and its per-element scale */
+    nn_mat D1; const float* db1;
+    nn_mat D2; const float* db2;
+    nn_mat D3; const float* db3;
+    const float* dscale;            /* scalers.k.scale.weight [119] of the direct_force head, or NULL = head absent */
 } nn_weights;
 
 /* ------------------------------------------------------------------ neighbour list
@@ -200,6 +206,7 @@ typedef struct {
     float* stress;                  /* [B,9] or NULL */
     float* atom_node;               /* [N,F]   final invariant features (CustomOutputSet.atom_node) */
     float* force_node;              /* [N,3,F] final equivariant features */
+    float* direct_force;            /* [N,3] direct_force head output, or NULL */
     void* workspace; size_t workspace_bytes;   /* nn_eval_workspace_bytes() */
 } nn_eval_args;
 NN_API size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, int32_t cap_pairs, int32_t n_layers,

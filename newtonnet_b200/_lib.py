@@ -32,13 +32,14 @@ class Mat(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [('W1', Mat), ('b1', _fp), ('W2', Mat), ('b2', _fp), ('We', _fp), ('Wet', _fp), ('We_img', _fp),
-                ('U1', Mat), ('U2', Mat), ('V1', Mat), ('V2', Mat), ('Wu', Mat)]
+                ('U1', Mat), ('U2', Mat), ('V1', Mat), ('V2', Mat), ('Wu', Mat), ('ln_gamma', _fp), ('ln_beta', _fp)]
 
 
 class Weights(C.Structure):
     _fields_ = [('n_layers', C.c_int32), ('cutoff', C.c_float), ('embedding', _fp), ('frequencies', _fp),
                 ('layer', LayerWeights * NN_MAX_LAYERS), ('H1', Mat), ('hb1', _fp), ('H2', Mat), ('hb2', _fp),
-                ('w3', _fp), ('hb3', _fp), ('scale', _fp), ('shift', _fp)]
+                ('w3', _fp), ('hb3', _fp), ('scale', _fp), ('shift', _fp),
+                ('D1', Mat), ('db1', _fp), ('D2', Mat), ('db2', _fp), ('D3', Mat), ('db3', _fp), ('dscale', _fp)]
 
 
 class Nbr(C.Structure):
@@ -57,7 +58,7 @@ class GemmArgs(C.Structure):
 class EvalArgs(C.Structure):
     _fields_ = [('nbr', C.POINTER(Nbr)), ('w', C.POINTER(Weights)), ('z', _fp), ('want_forces', C.c_int32),
                 ('want_virial', C.c_int32), ('n_owned', C.c_int32), ('pad_', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
-                ('atom_node', _fp), ('force_node', _fp), ('workspace', _fp), ('workspace_bytes', C.c_size_t)]
+                ('atom_node', _fp), ('force_node', _fp), ('direct_force', _fp), ('workspace', _fp), ('workspace_bytes', C.c_size_t)]
 
 
 # every symbol include/newtonnet_b200.h declares: name -> (restype, argtypes)

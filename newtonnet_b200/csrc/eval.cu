@@ -18,6 +18,9 @@ int nn_pair_bwd_gather_launch(const nn_nbr* nl, const float* dfb, const float* f
                               float* e2bar, float* ubar, bool first, cudaStream_t s);
 int nn_pair_bwd_message_launch(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
                                const float* Wet, float* mbar_io, float* x_bar, cudaStream_t s);
+int nn_layer_norm_fwd_launch(float* a_io, const float* gamma, const float* beta, float* xhat, float* rstd, int n_rows, cudaStream_t s);
+int nn_layer_norm_bwd_launch(float* abar_io, const float* gamma, const float* xhat, const float* rstd, int n_rows, cudaStream_t s);
+int nn_direct_force_launch(const float* h, const float* f, const float* scale, const int64_t* z, int n_rows, float* out, cudaStream_t s);
 int nn_message_fwd_tc(const nn_nbr* nl, const float* rbf, const float* mn, const float* We_img, float* msg, cudaStream_t s);
 int nn_message_bwd_tc(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
                       const float* We_img, float* mbar_io, float* x_part, cudaStream_t s);
@@ -111,6 +114,7 @@ namespace {
 struct LayerBuf {
     float *pre, *mn, *f_out, *g;          // node level: [N,F], [N,F], [N,3,F], [N,3,F]
     float *msg, *q1, *e1, *q2, *e2;       // pair level: [P,F] each (q2/e2 unused in layer 0)
+    float *ln_xhat, *ln_rstd;             // layer norm: normalised rows [N,F] and 1/sigma [N]
 };
 
 struct EvalWs {
@@ -118,6 +122,7 @@ struct EvalWs {
     float *a0, *a1;                       // [N,F] ping-pong invariant features
     float *rbf, *drbf, *unit, *dist;      // [P,nb], [P,nb] (d rbf / dx), [P,3], [P]
     float *h1pre, *h2pre, *e_atom;        // head
+    float *d1, *d2;                       // direct_force head temporaries [N,F]
     // reverse sweep
     float *abar, *mnbar, *tmpN;           // [N,F]
     float *fbar, *dfb;                    // [N,3,F]
@@ -137,11 +142,13 @@ EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
         b.f_out = c.take<float>(3 * NF); b.g = c.take<float>(3 * NF);
         b.msg = c.take<float>(PF); b.q1 = c.take<float>(PF); b.e1 = c.take<float>(PF);
         if (l > 0) { b.q2 = c.take<float>(PF); b.e2 = c.take<float>(PF); }
+        b.ln_xhat = c.take<float>(NF); b.ln_rstd = c.take<float>(N);
     }
     w.a0 = c.take<float>(NF); w.a1 = c.take<float>(NF);
     w.rbf = c.take<float>((size_t)P * kNB); w.unit = c.take<float>((size_t)P * 3); w.dist = c.take<float>(P);
     w.drbf = bwd ? c.take<float>((size_t)P * kNB) : nullptr;
     w.h1pre = c.take<float>(NF); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
+    w.d1 = c.take<float>(NF); w.d2 = c.take<float>(NF);
     if (bwd) {
         w.abar = c.take<float>(NF); w.mnbar = c.take<float>(NF); w.tmpN = c.take<float>(NF);
         w.fbar = c.take<float>(3 * NF); w.dfb = c.take<float>(3 * NF);
@@ -262,6 +269,10 @@ int run_phase(EvalCtx& c, int phase, int l) {
         g.fwd(b.f_out, lw.Wu, b.g, 3 * No, NN_PRO_NONE, NN_EPI_BIAS);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, No, s)); }
+        if (lw.ln_gamma) {   // layer_norm=True (models/newtonnet.py:234-235)
+            ProfScope ps(NN_STAGE_OTHER, s);
+            NN_TRY(nn_layer_norm_fwd_launch(a_cur, lw.ln_gamma, lw.ln_beta, b.ln_xhat, b.ln_rstd, No, s));
+        }
         return 0;
     }
     case NN_PH_HEAD: {       // energy head (R8, R9): partial energies over owned atoms
@@ -269,6 +280,15 @@ int run_phase(EvalCtx& c, int phase, int l) {
         g.fwd(w.h1pre, W.H2, w.h2pre, No, c.PRO_ACT, NN_EPI_BIAS, W.hb2);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd_rows(w.h2pre, W.w3, W.hb3, W.scale, W.shift, c.a->z, nl->sys_ptr, No, c.B, w.e_atom, c.a->energy, s)); }
+        if (c.a->direct_force) {   // direct_force head (models/output.py:115-132): no reverse sweep involved
+            NN_REQUIRE(W.dscale != nullptr, "direct_force requested but the weights carry no direct_force head");
+            g.fwd(a_cur, W.D1, w.d1, No, NN_PRO_NONE, NN_EPI_BIAS, W.db1);
+            g.fwd(w.d1, W.D2, w.d2, No, NN_PRO_SILU, NN_EPI_BIAS, W.db2);
+            g.fwd(w.d2, W.D3, w.d1, No, NN_PRO_SILU, NN_EPI_BIAS, W.db3);
+            NN_TRY(g.rc);
+            ProfScope ps(NN_STAGE_HEAD, s);
+            NN_TRY(nn_direct_force_launch(w.d1, w.layer[L - 1].f_out, W.dscale, c.a->z, No, c.a->direct_force, s));
+        }
         if (c.a->atom_node) cudaMemcpyAsync(c.a->atom_node, a_cur, (size_t)No * kF * sizeof(float), cudaMemcpyDeviceToDevice, s);
         if (c.a->force_node) cudaMemcpyAsync(c.a->force_node, w.layer[L - 1].f_out, (size_t)No * 3 * kF * sizeof(float),
                                              cudaMemcpyDeviceToDevice, s);
@@ -286,6 +306,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
     }
     case NN_PH_BWD_NODE: {   // dfb = fbar + abar*g + (abar*f_out) @ Wu  (owned)   [then ghosts of: dfb, abar]
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
+        if (lw.ln_gamma) NN_TRY(nn_layer_norm_bwd_launch(w.abar, lw.ln_gamma, b.ln_xhat, b.ln_rstd, No, s));
         g.bwd(b.f_out, lw.Wu, w.dfb, 3 * No, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, w.fbar, w.abar, b.g);
         return g.rc;
     }

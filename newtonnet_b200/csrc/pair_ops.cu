@@ -209,6 +209,57 @@ __global__ void k_embed(const int64_t* __restrict__ z, const float* __restrict__
     st4(a + (size_t)i * kF + q, ld4(emb + (size_t)zi * kF + q));
 }
 
+// ---------------------------------------------------------------------------- layer norm (layer_norm=True)
+// nn.LayerNorm(F) on atom_node at the end of a layer (models/newtonnet.py:234-235): eps 1e-5, biased variance.
+__global__ void __launch_bounds__(kThreads)
+k_layer_norm_fwd(float* __restrict__ a_io, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float* __restrict__ xhat, float* __restrict__ rstd, int n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= n_rows) return;
+    float4 x = ld4(a_io + (size_t)i * kF + 4 * lane);
+    const float mean = warp_sum(x.x + x.y + x.z + x.w) * (1.0f / kF);
+    const float4 d = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
+    const float var = warp_sum(f4_dot(d, d)) * (1.0f / kF);
+    const float r = rsqrtf(var + 1e-5f);
+    const float4 h = make_float4(d.x * r, d.y * r, d.z * r, d.w * r);
+    if (xhat) st4(xhat + (size_t)i * kF + 4 * lane, h);
+    if (rstd && lane == 0) rstd[i] = r;
+    st4(a_io + (size_t)i * kF + 4 * lane, f4_fma(h, ld4(gamma + 4 * lane), ld4(beta + 4 * lane)));
+}
+// abar_in = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = abar_out * gamma
+__global__ void __launch_bounds__(kThreads)
+k_layer_norm_bwd(float* __restrict__ abar_io, const float* __restrict__ gamma, const float* __restrict__ xhat,
+                 const float* __restrict__ rstd, int n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= n_rows) return;
+    const float4 g = f4_mul(ld4(abar_io + (size_t)i * kF + 4 * lane), ld4(gamma + 4 * lane));
+    const float4 h = ld4(xhat + (size_t)i * kF + 4 * lane);
+    const float m1 = warp_sum(g.x + g.y + g.z + g.w) * (1.0f / kF);
+    const float m2 = warp_sum(f4_dot(g, h)) * (1.0f / kF);
+    const float r = rstd[i];
+    st4(abar_io + (size_t)i * kF + 4 * lane, make_float4(r * (g.x - m1 - h.x * m2), r * (g.y - m1 - h.y * m2),
+                                                          r * (g.z - m1 - h.z * m2), r * (g.w - m1 - h.w * m2)));
+}
+
+// direct_force head tail (models/output.py:129-131 + scalers.py:55-56): F_i[c] = scale[z_i] * <h_i, f_i[c]>
+__global__ void __launch_bounds__(kThreads)
+k_direct_force(const float* __restrict__ h, const float* __restrict__ f, const float* __restrict__ scale,
+               const int64_t* __restrict__ z, int n_rows, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= n_rows) return;
+    const float4 hv = ld4(h + (size_t)i * kF + 4 * lane);
+    const float* fi = f + (size_t)i * 3 * kF + 4 * lane;
+    const float sx = warp_sum(f4_dot(hv, ld4(fi))), sy = warp_sum(f4_dot(hv, ld4(fi + kF))), sz = warp_sum(f4_dot(hv, ld4(fi + 2 * kF)));
+    if (lane == 0) {
+        long long zi = z[i]; if (zi < 0 || zi > 118) zi = 0;
+        const float sc = scale[zi];
+        out[3 * i] = sc * sx; out[3 * i + 1] = sc * sy; out[3 * i + 2] = sc * sz;
+    }
+}
+
 // ---------------------------------------------------------------------------- energy head
 __global__ void __launch_bounds__(kThreads)
 k_energy_atom(const float* __restrict__ h2pre, const float* __restrict__ w3, const float* __restrict__ b3,
@@ -657,6 +708,24 @@ extern "C" int nn_halo_pack(const float* src, const int32_t* idx, int32_t n, int
 }
 
 // ---- launchers used only by nn_eval (eval.cu)
+int nn_layer_norm_fwd_launch(float* a_io, const float* gamma, const float* beta, float* xhat, float* rstd, int n_rows, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    k_layer_norm_fwd<<<nn_ceil_div(n_rows, kWarps), kThreads, 0, s>>>(a_io, gamma, beta, xhat, rstd, n_rows); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("layer_norm_fwd");
+    return 0;
+}
+int nn_layer_norm_bwd_launch(float* abar_io, const float* gamma, const float* xhat, const float* rstd, int n_rows, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    k_layer_norm_bwd<<<nn_ceil_div(n_rows, kWarps), kThreads, 0, s>>>(abar_io, gamma, xhat, rstd, n_rows); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("layer_norm_bwd");
+    return 0;
+}
+int nn_direct_force_launch(const float* h, const float* f, const float* scale, const int64_t* z, int n_rows, float* out, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    k_direct_force<<<nn_ceil_div(n_rows, kWarps), kThreads, 0, s>>>(h, f, scale, z, n_rows, out); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("direct_force");
+    return 0;
+}
 int nn_embed_launch(const int64_t* z, const float* emb, float* a, int N, int* status, cudaStream_t s) {
     if (N <= 0) return 0;
     k_embed<<<nn_ceil_div((long long)N * (kF / 4), 256), 256, 0, s>>>(z, emb, a, N, status); NN_LAUNCHED(1);

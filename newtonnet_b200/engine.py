@@ -71,9 +71,10 @@ class WeightPack:
         w.frequencies = f32(freq).data_ptr()
         for l in range(n_layers):
             k = f'interaction_layers.{l}.'
-            if (k + 'layer_norm.weight') in state:
-                raise NotImplementedError('layer_norm=True is not supported by the CUDA path yet')
             lw = w.layer[l]
+            if (k + 'layer_norm.weight') in state:
+                lw.ln_gamma = f32(state[k + 'layer_norm.weight']).data_ptr()
+                lw.ln_beta = f32(state[k + 'layer_norm.bias']).data_ptr()
             mat(lw.W1, state[k + 'message_nodepart.0.weight'])
             lw.b1 = f32(state[k + 'message_nodepart.0.bias']).data_ptr()
             mat(lw.W2, state[k + 'message_nodepart.2.weight'])
@@ -101,6 +102,12 @@ class WeightPack:
         w.hb3 = f32(state[h + '4.bias'].reshape(-1)).data_ptr()
         w.scale = f32(state[f'scalers.{idx}.scale.weight'].reshape(-1)).data_ptr()
         w.shift = f32(state[f'scalers.{idx}.shift.weight'].reshape(-1)).data_ptr()
+        self.has_direct_force = 'direct_head.layers.0.weight' in state
+        if self.has_direct_force:
+            mat(w.D1, state['direct_head.layers.0.weight']); w.db1 = f32(state['direct_head.layers.0.bias']).data_ptr()
+            mat(w.D2, state['direct_head.layers.2.weight']); w.db2 = f32(state['direct_head.layers.2.bias']).data_ptr()
+            mat(w.D3, state['direct_head.layers.4.weight']); w.db3 = f32(state['direct_head.layers.4.bias']).data_ptr()
+            w.dscale = f32(state['direct_head.scale'].reshape(-1)).data_ptr()
         self.struct = w
         self.n_layers = n_layers
         self.cutoff = float(cutoff)
@@ -238,7 +245,7 @@ class Engine:
             self._ws = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def evaluate(self, nl, weights, z, want_forces=True, want_virial=False, want_nodes=False):
+    def evaluate(self, nl, weights, z, want_forces=True, want_virial=False, want_nodes=False, want_direct=False):
         _require_cuda(z, 'z')
         z = z.to(torch.int64).contiguous()
         N, B = nl.n_atoms, nl.n_systems
@@ -254,6 +261,8 @@ class Engine:
         if want_nodes:
             out['atom_node'] = torch.empty(N, L.NN_F, **f32)
             out['force_node'] = torch.empty(N, 3, L.NN_F, **f32)
+        if want_direct:
+            out['direct_force'] = torch.empty(N, 3, **f32)
         nbytes = self.lib.nn_eval_workspace_bytes(N, B, nl.cap_pairs, weights.n_layers, int(bwd))
         ws = self._workspace(nbytes)
         a = L.EvalArgs()
@@ -267,18 +276,20 @@ class Engine:
         a.stress = L.ptr(out.get('stress'))
         a.atom_node = L.ptr(out.get('atom_node'))
         a.force_node = L.ptr(out.get('force_node'))
+        a.direct_force = L.ptr(out.get('direct_force'))
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         L.check(self.lib.nn_eval(C.byref(a), _stream()), 'nn_eval')
         out['_z'] = z   # keep alive until the stream has consumed it
         return out
 
-    def energy_forces(self, weights, z, pos, cell, batch, want_forces=True, want_virial=False, want_nodes=False):
+    def energy_forces(self, weights, z, pos, cell, batch, want_forces=True, want_virial=False, want_nodes=False,
+                      want_direct=False):
         """Neighbour list + evaluation + status check, regrowing capacities when needed.  From the second
         call with the same shapes on, the whole step (neighbour rebuild + ~80 kernels) is replayed as one
         CUDA graph."""
         if self.use_cuda_graphs:
             key = (pos.shape[0], cell.reshape(-1, 9).shape[0], bool(want_forces), bool(want_virial), bool(want_nodes),
-                   id(weights), str(pos.device))
+                   bool(want_direct), id(weights), str(pos.device))
             g = self._graphs.get(key)
             if g is not None:
                 out = g.replay(z, pos, cell, batch)
@@ -289,18 +300,18 @@ class Engine:
                 if len(self._graphs) >= 4:
                     self._graphs.pop(next(iter(self._graphs)))
                 self._graphs[key] = GraphedStep(self, weights, z, pos, cell, batch, want_forces, want_virial, want_nodes,
-                                                self._nl.cap_edges)
+                                                self._nl.cap_edges, want_direct)
                 out = self._graphs[key].replay(z, pos, cell, batch)
                 if out is not None:
                     return out
                 del self._graphs[key]
             self._last_key = key
         nl = self.neighbor_list(pos, cell, batch, weights.cutoff)
-        out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes)
+        out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes, want_direct)
         st = nl.check()
         if st[L.ST_EDGE_OVERFLOW]:
             nl = self.grow(nl, weights.cutoff, max(st[L.ST_EDGE_OVERFLOW], st[L.ST_N_EDGES]))
-            out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes)
+            out = self.evaluate(nl, weights, z, want_forces, want_virial, want_nodes, want_direct)
             st = nl.check()
             if st[L.ST_EDGE_OVERFLOW]:
                 raise RuntimeError('neighbour list capacity overflow after regrow')
@@ -311,7 +322,8 @@ class Engine:
 class GraphedStep:
     """One evaluation (neighbour rebuild + nn_eval) captured as a CUDA graph over static buffers."""
 
-    def __init__(self, engine, weights, z, pos, cell, batch, want_forces, want_virial, want_nodes, cap_edges):
+    def __init__(self, engine, weights, z, pos, cell, batch, want_forces, want_virial, want_nodes, cap_edges,
+                 want_direct=False):
         dev = pos.device
         self.engine, self.weights = engine, weights
         self.z = torch.empty(z.shape, dtype=torch.int64, device=dev)
@@ -332,6 +344,8 @@ class GraphedStep:
         if want_nodes:
             self.out['atom_node'] = torch.empty(N, L.NN_F, **f32)
             self.out['force_node'] = torch.empty(N, 3, L.NN_F, **f32)
+        if want_direct:
+            self.out['direct_force'] = torch.empty(N, 3, **f32)
         nbytes = engine.lib.nn_eval_workspace_bytes(N, B, self.nl.cap_pairs, weights.n_layers, int(bwd))
         self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         a = L.EvalArgs()
@@ -340,6 +354,7 @@ class GraphedStep:
         a.energy = self.out['energy'].data_ptr()
         a.forces, a.virial, a.stress = L.ptr(self.out.get('forces')), L.ptr(self.out.get('virial')), L.ptr(self.out.get('stress'))
         a.atom_node, a.force_node = L.ptr(self.out.get('atom_node')), L.ptr(self.out.get('force_node'))
+        a.direct_force = L.ptr(self.out.get('direct_force'))
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
         self.args = a
         torch.cuda.synchronize(dev)

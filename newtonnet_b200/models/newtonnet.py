@@ -15,15 +15,15 @@ from newtonnet_b200.models.output import (CustomOutputSet, DerivativeProperty, g
 
 __all__ = ['NewtonNet', 'EmbeddingNet', 'InteractionNet']
 
-_SUPPORTED = ('energy', 'gradient_force', 'stress', 'virial')
+_SUPPORTED = ('energy', 'gradient_force', 'stress', 'virial', 'direct_force')
 
 
 class NewtonNet(nn.Module):
     """Molecular Newtonian message passing (reference models/newtonnet.py:12-71).
 
     Parameters are those of the reference: cutoff, n_features, n_basis, n_interactions, activation,
-    layer_norm, output_properties.  The kernels are specialised for n_features=128, n_basis=20, SiLU and
-    layer_norm=False (scripts/config.yml:30-35); other values raise at the first forward.
+    layer_norm, output_properties.  The kernels are specialised for n_features=128, n_basis=20 and SiLU
+    (scripts/config.yml:30-35); other values raise at the first forward.
     """
 
     def __init__(self, cutoff: float = 5.0, n_features: int = 128, n_basis: int = 20, n_interactions: int = 3,
@@ -67,11 +67,16 @@ class NewtonNet(nn.Module):
             i = head[0]
             # the pack reads head / scaler parameters under index 0
             remap = {}
+            d = [j for j, k in enumerate(self.output_properties) if k == 'direct_force']
             for k, t in sd.items():
                 if k.startswith(f'output_layers.{i}.'):
                     remap['output_layers.0.' + k[len(f'output_layers.{i}.'):]] = t
                 elif k.startswith(f'scalers.{i}.'):
                     remap['scalers.0.' + k[len(f'scalers.{i}.'):]] = t
+                elif d and k.startswith(f'output_layers.{d[0]}.'):
+                    remap['direct_head.' + k[len(f'output_layers.{d[0]}.'):]] = t
+                elif d and k == f'scalers.{d[0]}.scale.weight':
+                    remap['direct_head.scale'] = t
                 elif not (k.startswith('output_layers.') or k.startswith('scalers.')):
                     remap[k] = t
             self._pack = WeightPack(remap, self.cutoff, device)
@@ -85,7 +90,7 @@ class NewtonNet(nn.Module):
         z [N] int64 atomic numbers, pos [N,3], cell [B,3,3] (zeros = not periodic), batch [N] int64
         non-decreasing system index.  Returns a CustomOutputSet with z, pos, cell, batch, displacement,
         atom_node, force_node, edge_index and one attribute per entry of `output_properties`:
-        energy [B], gradient_force [N,3], stress [B,3,3], virial [B,3,3].
+        energy [B], gradient_force [N,3], stress [B,3,3], virial [B,3,3], direct_force [N,3].
         """
         from newtonnet_b200.engine import get_engine
         props = list(self.output_properties)
@@ -97,7 +102,7 @@ class NewtonNet(nn.Module):
             return differentiable_forward(self, z, pos, cell, batch)
         if not pos.is_cuda:
             raise RuntimeError('newtonnet_b200: inputs must be CUDA tensors - there is no CPU fallback')
-        derivative = [k for k in props if k != 'energy']
+        derivative = [k for k in props if k not in ('energy', 'direct_force')]
         if derivative and props.index('energy') > min(props.index(k) for k in derivative):
             raise AttributeError("'CustomOutputSet' object has no attribute 'energy'")   # as the reference
         if self.embedding_layers.requires_dr and pos.is_leaf and not pos.requires_grad and pos.is_floating_point():
@@ -107,7 +112,7 @@ class NewtonNet(nn.Module):
         engine = get_engine(pos.device)
         pack = self._weight_pack(pos.device)
         res = engine.energy_forces(pack, z, pos, cell, batch, want_forces=want_forces, want_virial=want_virial,
-                                   want_nodes=self.return_node_features)
+                                   want_nodes=self.return_node_features, want_direct='direct_force' in props)
         dt = pos.dtype
         nl = res['_nl']
         displacement = torch.eye(3, dtype=dt, device=pos.device).repeat(cell.shape[0], 1, 1)
@@ -128,6 +133,8 @@ class NewtonNet(nn.Module):
                 value = res['forces'].to(dt)
             elif key == 'virial':
                 value = res['virial'].to(dt)
+            elif key == 'direct_force':
+                value = res['direct_force'].to(dt)
             else:
                 value = res['stress'].to(dt)
             setattr(outputs, key, value)

@@ -1,8 +1,8 @@
 """Output heads, scalers' companions and the result bag; mirrors newtonnet/models/output.py.
 
-Supported heads (the hot path of BASELINE.json): 'energy', 'gradient_force', 'stress', 'virial'.
-'direct_force', 'hessian', 'charge', 'bec' raise NotImplementedError (out of
-scope; charge/bec need the un-vendored `les` package).
+Supported heads (the hot path of BASELINE.json): 'energy', 'gradient_force', 'stress', 'virial', plus
+'direct_force' (SURVEY.md section 8f rank 2).  'hessian', 'charge', 'bec' raise NotImplementedError
+(out of scope; charge/bec need the un-vendored `les` package).
 
 The heads own parameters and flags only.  Energies, forces and virials are produced together by one
 nn_eval call (csrc/eval.cu); NewtonNet.forward distributes the results to the bag in the order of
@@ -12,10 +12,10 @@ import torch
 from torch import nn
 
 __all__ = ['get_output_by_string', 'get_aggregator_by_string', 'CustomOutputSet', 'DirectProperty',
-           'DerivativeProperty', 'SecondDerivativeProperty', 'EnergyOutput', 'GradientForceOutput',
+           'DerivativeProperty', 'SecondDerivativeProperty', 'EnergyOutput', 'GradientForceOutput', 'DirectForceOutput',
            'VirialOutput', 'StressOutput', 'EnergyAggregator', 'NullAggregator', 'SumAggregator']
 
-_UNSUPPORTED = ('direct_force', 'hessian', 'charge', 'bec')
+_UNSUPPORTED = ('hessian', 'charge', 'bec')
 
 
 def get_output_by_string(key, n_features=None, activation=None):
@@ -23,6 +23,8 @@ def get_output_by_string(key, n_features=None, activation=None):
         return EnergyOutput(n_features, activation)
     if key == 'gradient_force':
         return GradientForceOutput()
+    if key == 'direct_force':
+        return DirectForceOutput(n_features, activation)
     if key == 'virial':
         return VirialOutput()
     if key == 'stress':
@@ -35,7 +37,7 @@ def get_output_by_string(key, n_features=None, activation=None):
 def get_aggregator_by_string(key):
     if key == 'energy':
         return EnergyAggregator()
-    if key in ('gradient_force', 'virial', 'stress'):
+    if key in ('gradient_force', 'direct_force', 'virial', 'stress'):
         return NullAggregator()
     if key in _UNSUPPORTED:
         raise NotImplementedError(f"output '{key}' is outside the B200 energy/force/stress path")
@@ -84,6 +86,22 @@ class EnergyOutput(DirectProperty):
             nn.Linear(n_features, n_features), act,
             nn.Linear(n_features, n_features), act,
             nn.Linear(n_features, 1),
+        )
+
+
+class DirectForceOutput(DirectProperty):
+    """force_i[c] = sum_f MLP(atom_node_i)[f] * force_node_i[c][f]  (models/output.py:115-132); parameters only,
+    evaluated by nn_eval (three GEMMs + k_direct_force)."""
+
+    def __init__(self, n_features, activation):
+        super().__init__()
+        if n_features is None:
+            raise ValueError("get_output_by_string('direct_force') needs n_features")
+        act = activation if activation is not None else nn.SiLU()
+        self.layers = nn.Sequential(
+            nn.Linear(n_features, n_features), act,
+            nn.Linear(n_features, n_features), act,
+            nn.Linear(n_features, n_features),
         )
 
 

@@ -167,8 +167,8 @@ def differentiable_forward(model, z, pos, cell, batch):
     if 'energy' not in props:
         raise RuntimeError("output_properties must contain 'energy'")
     for key in props:
-        if key not in ('energy', 'gradient_force'):
-            raise NotImplementedError(f"training-mode evaluation supports energy and gradient_force, not '{key}'")
+        if key not in ('energy', 'gradient_force', 'direct_force'):
+            raise NotImplementedError(f"training-mode evaluation supports energy, gradient_force and direct_force, not '{key}'")
     if not pos.is_cuda:
         raise RuntimeError('newtonnet_b200: inputs must be CUDA tensors - there is no CPU fallback')
     if pos.dtype != torch.float32 or next(model.parameters()).dtype != torch.float32:
@@ -199,8 +199,6 @@ def differentiable_forward(model, z, pos, cell, batch):
     a = Fn.embedding(z, emb.node_embedding.weight, padding_idx=0)
     f = torch.zeros(N, 3 * F, dtype=torch.float32, device=dev)
     for layer in model.interaction_layers:
-        if layer.layer_norm is not None:
-            raise NotImplementedError('layer_norm=True is not supported by the CUDA path yet')
         n0, n2 = layer.message_nodepart[0], layer.message_nodepart[2]
         mn = linear(Fn.silu(linear(a, n0.weight, n0.bias)), n2.weight, n2.bias)
         # K = 20 contraction through the same fp32-faithful GEMM (zero-padded to K = 128): a library matmul may
@@ -215,6 +213,8 @@ def differentiable_forward(model, z, pos, cell, batch):
         f = f + SegmentSum.apply(vec.reshape(-1, 3 * F), seg_dst)
         g = linear(f.view(3 * N, F), layer.equiv_update.weight).view(N, 3, F)
         a = a + (f.view(N, 3, F) * g).sum(1)
+        if layer.layer_norm is not None:
+            a = Fn.layer_norm(a, (F,), layer.layer_norm.weight, layer.layer_norm.bias, layer.layer_norm.eps)
     k = props.index('energy')
     head, scaler = model.output_layers[k].layers, model.scalers[k]
     h = Fn.silu(linear(a, head[0].weight, head[0].bias))
@@ -227,6 +227,12 @@ def differentiable_forward(model, z, pos, cell, batch):
     for key in props:
         if key == 'energy':
             out.energy = energy
+        elif key == 'direct_force':
+            kd = props.index(key)
+            dl, ds = model.output_layers[kd].layers, model.scalers[kd]
+            hd = Fn.silu(linear(a, dl[0].weight, dl[0].bias))
+            hd = linear(Fn.silu(linear(hd, dl[2].weight, dl[2].bias)), dl[4].weight, dl[4].bias)
+            out.direct_force = (hd.unsqueeze(1) * f.view(N, 3, F)).sum(-1) * ds.scale(z)
         else:
             create = bool(model.output_layers[props.index(key)].create_graph)
             out.pos_grad, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=create,

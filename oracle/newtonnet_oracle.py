@@ -197,6 +197,8 @@ def interaction(sd, l, a, f, direction, rbf, edge_index):
     vec = e1.unsqueeze(1) * direction.unsqueeze(2) + e2.unsqueeze(1) * f[j]                   # :219-224
     f = f + _segment_sum(vec, i, n)                                                           # :226-227
     a = a + (f * (f @ sd[k + 'equiv_update.weight'].T)).sum(dim=1)                            # :230-231
+    if (k + 'layer_norm.weight') in sd:                                                       # :234-235, nn.LayerNorm(F)
+        a = torch.nn.functional.layer_norm(a, (a.shape[1],), sd[k + 'layer_norm.weight'], sd[k + 'layer_norm.bias'], 1e-5)
     return a, f
 
 
@@ -210,9 +212,19 @@ def atomic_energy(sd, a, z, head=0):
     return o * sd[f'scalers.{head}.scale.weight'][z] + sd[f'scalers.{head}.shift.weight'][z]
 
 
+def direct_force(sd, a, f, z, head):
+    """DirectForceOutput (models/output.py:115-132) + ScaleShift(scale only) (layers/scalers.py:11,55-56):
+    F_i[c] = scale[z_i] * sum_f MLP(a_i)[f] * f_i[c][f]."""
+    k = f'output_layers.{head}.layers.'
+    h = silu(a @ sd[k + '0.weight'].T + sd[k + '0.bias'])
+    h = silu(h @ sd[k + '2.weight'].T + sd[k + '2.bias'])
+    h = h @ sd[k + '4.weight'].T + sd[k + '4.bias']
+    return (h.unsqueeze(1) * f).sum(-1) * sd[f'scalers.{head}.scale.weight'][z]
+
+
 # ----------------------------------------------------------------------------- R0/R1/R10 full path
 def forward(sd, z, pos, cell, batch, dtype=torch.float64, stress=False, return_layers=False,
-            cutoff=CUTOFF):
+            cutoff=CUTOFF, direct_force_head=None):
     """NewtonNet.forward, models/newtonnet.py:74-104, heads energy + gradient_force (+ stress/virial).
 
     Follows the reference's strain trick (models/newtonnet.py:146-155): D = I, S = (D + D^T)/2,
@@ -250,6 +262,8 @@ def forward(sd, z, pos, cell, batch, dtype=torch.float64, stress=False, return_l
         out['stress'] = (g_D / torch.linalg.det(cell).view(-1, 1, 1)).numpy()
     if return_layers:
         out['layers'] = layers
+    if direct_force_head is not None:
+        out['direct_force'] = direct_force(sd, a, f, z, direct_force_head).detach().numpy()
     return out
 
 

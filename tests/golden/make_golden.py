@@ -318,9 +318,47 @@ def training_golden():
         print(f'train_{name}: loss {loss.item():.6f} |grad| {gn:.4f}')
 
 
+def widening_golden():
+    """layer_norm=True and the direct_force head.  Weights = weights_seed0 plus small
+    extra tensors stored in the case file (layer-norm affine parameters / direct-force head)."""
+    sd0 = dict(np.load(f'{OUT}/weights_seed0.npz'))
+    g = torch.Generator().manual_seed(77)
+    extra = {}
+    for l in range(3):
+        extra[f'interaction_layers.{l}.layer_norm.weight'] = (1.0 + 0.3 * torch.randn(128, generator=g)).numpy()
+        extra[f'interaction_layers.{l}.layer_norm.bias'] = (0.2 * torch.randn(128, generator=g)).numpy()
+    torch.manual_seed(3)
+    probe = NewtonNet(output_properties=['energy', 'gradient_force', 'direct_force'])
+    for k, v in probe.state_dict().items():
+        if k.startswith('output_layers.2.') or k.startswith('scalers.2.'):
+            extra[k] = v.detach().numpy().copy()
+    extra['scalers.2.scale.weight'] = (torch.rand(119, 1, generator=g) + 0.5).numpy()
+    for name, (z, p, c, b) in {'mols_edge': molecule_batch(0, seed=7, sizes=[1, 2, 64, 3, 1, 17, 64, 5]),
+                               'water81': water_box(3)}.items():
+        for dtype, tag in ((torch.float64, 'ref64'), (torch.float32, 'ref32')):
+            m = NewtonNet(layer_norm=True, output_properties=['energy', 'gradient_force', 'direct_force'])
+            sd = {k: torch.as_tensor(v) for k, v in {**sd0, **extra}.items()}
+            m.load_state_dict(sd, strict=True)
+            m = m.to(dtype); m.eval()
+            out = m(z, p.to(dtype).clone(), c.to(dtype), b)
+            if tag == 'ref64':
+                d = dict(z=z.numpy(), pos=p.numpy().astype(np.float32), cell=c.numpy().astype(np.float32), batch=b.numpy())
+                d.update({'extra.' + k: v for k, v in extra.items()})
+            d[f'{tag}_energy'] = out.energy.detach().numpy()
+            d[f'{tag}_forces'] = out.gradient_force.detach().numpy()
+            d[f'{tag}_direct_force'] = out.direct_force.detach().numpy()
+            d[f'{tag}_atom_node'] = out.atom_node.detach().numpy().astype(np.float32)
+        np.savez_compressed(f'{OUT}/wide_{name}.npz', **d)
+        print(f'wide_{name}: E {d["ref64_energy"][:2]} |F|max {np.abs(d["ref64_forces"]).max():.3f} '
+              f'|DF|max {np.abs(d["ref64_direct_force"]).max():.3f} 32-vs-64 dF {np.abs(d["ref32_forces"]-d["ref64_forces"]).max():.2e}')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+    if len(sys.argv) > 1 and sys.argv[1] == 'wide':
+        widening_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'train':
         training_golden()
     else:
         main()
         training_golden()
+        widening_golden()

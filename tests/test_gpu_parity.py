@@ -309,6 +309,29 @@ def test_other_hyperparameters_against_oracle():
     assert np.abs(s_got - s_ref).max() < 1e-4 * np.abs(s_ref).max()
 
 
+@pytest.mark.parametrize('name', ['mols_edge', 'water81'])
+def test_layer_norm_and_direct_force(backend, name):
+    """layer_norm=True and the direct_force head against the unmodified reference; also the
+    training-mode (autograd-composed) forward of the same model."""
+    from newtonnet_b200.models import NewtonNet
+    d = dict(np.load(f'{GOLDEN}/wide_{name}.npz'))
+    w = load_weights('seed0')
+    w.update({k[6:]: v for k, v in d.items() if k.startswith('extra.')})
+    model = NewtonNet(layer_norm=True, output_properties=['energy', 'gradient_force', 'direct_force'])
+    model.load_state_dict({k: torch.tensor(v) for k, v in w.items()}, strict=True)
+    model = model.to(dev()); model.eval()
+    out = run_model(model, d)
+    np.testing.assert_allclose(out.energy.cpu().double().numpy(), d['ref64_energy'], rtol=E_RTOL, atol=1e-4)
+    assert np.abs(out.gradient_force.cpu().double().numpy() - d['ref64_forces']).max() < F_ATOL
+    assert np.abs(out.direct_force.cpu().double().numpy() - d['ref64_direct_force']).max() < F_ATOL
+    assert np.abs(out.atom_node.cpu().numpy() - d['ref64_atom_node']).max() < 1e-4
+    model.train()
+    t = lambda a: torch.tensor(a, device=dev())
+    tr = model(t(d['z']), t(d['pos']).requires_grad_(True), t(d['cell']), t(d['batch']))
+    assert np.abs(tr.gradient_force.detach().cpu().double().numpy() - d['ref64_forces']).max() < F_ATOL
+    assert np.abs(tr.direct_force.detach().cpu().double().numpy() - d['ref64_direct_force']).max() < F_ATOL
+
+
 def test_head_order_and_energy_only():
     d, w = load_case('aspirin1')
     out = run_model(make_model(w, ['energy']), d)

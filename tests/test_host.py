@@ -24,8 +24,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     # struct layouts agree with the header (sizes computed independently with the C compiler rules)
     import ctypes as C
     assert C.sizeof(_lib.Mat) == 4 * 8
-    assert C.sizeof(_lib.LayerWeights) == 7 * 32 + 5 * 8
-    assert C.sizeof(_lib.Weights) == 8 + 2 * 8 + 8 * (7 * 32 + 5 * 8) + 2 * 32 + 6 * 8
+    assert C.sizeof(_lib.LayerWeights) == 7 * 32 + 7 * 8
+    assert C.sizeof(_lib.Weights) == 8 + 2 * 8 + 8 * (7 * 32 + 7 * 8) + 2 * 32 + 6 * 8 + 3 * 32 + 4 * 8
     assert C.sizeof(_lib.Nbr) == 6 * 4 + 13 * 8 + 8
     assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 4 * 4
     assert lib.nn_nbr_workspace_bytes(1000, 4) > 0
@@ -66,9 +66,12 @@ def test_factories_and_unsupported_heads():
     assert get_scaler_by_string('energy').scale is not None and get_scaler_by_string('stress').scale is None
     for key in ('gradient_force', 'stress', 'virial'):
         get_output_by_string(key); get_aggregator_by_string(key)
-    for key in ('charge', 'hessian', 'bec', 'direct_force'):
+    for key in ('charge', 'hessian', 'bec'):
         with pytest.raises(NotImplementedError):
             get_output_by_string(key, 128, torch.nn.SiLU())
+    assert len(list(get_output_by_string('direct_force', 128, torch.nn.SiLU()).parameters())) == 6
+    ln = NewtonNet(layer_norm=True, output_properties=['energy', 'gradient_force', 'direct_force'])
+    assert 'interaction_layers.2.layer_norm.bias' in ln.state_dict() and 'scalers.2.scale.weight' in ln.state_dict()
     with pytest.raises(NotImplementedError):
         NewtonNet(output_properties=['charge', 'energy'])
     m = NewtonNet(output_properties=['energy', 'gradient_force'])

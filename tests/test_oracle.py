@@ -114,3 +114,15 @@ def test_training_gradients_match_reference(name):
         assert np.abs(v - d['grad.' + k]).max() < 1e-9 * max(1.0, np.abs(d['grad.' + k]).max()), k
     # the dead layer-0 equiv_message2 gets exactly zero gradient
     assert np.abs(d['grad.interaction_layers.0.equiv_message2.0.weight']).max() == 0.0
+
+
+@pytest.mark.parametrize('name', ['mols_edge', 'water81'])
+def test_layer_norm_and_direct_force_match_reference(name):
+    """layer_norm=True and the direct_force head against the unmodified reference."""
+    d = dict(np.load(f'{GOLDEN}/wide_{name}.npz'))
+    w = load_weights('seed0')
+    w.update({k[6:]: v for k, v in d.items() if k.startswith('extra.')})
+    o = O.forward(w, d['z'], d['pos'], d['cell'], d['batch'], direct_force_head=2)
+    np.testing.assert_allclose(o['energy'], d['ref64_energy'], rtol=1e-12, atol=1e-10)
+    assert np.abs(o['forces'] - d['ref64_forces']).max() < 1e-12
+    assert np.abs(o['direct_force'] - d['ref64_direct_force']).max() < 1e-12
