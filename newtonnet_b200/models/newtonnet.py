@@ -15,7 +15,7 @@ from newtonnet_b200.models.output import (CustomOutputSet, DerivativeProperty, g
 
 __all__ = ['NewtonNet', 'EmbeddingNet', 'InteractionNet']
 
-_SUPPORTED = ('energy', 'gradient_force', 'stress', 'virial', 'direct_force')
+_SUPPORTED = ('energy', 'gradient_force', 'stress', 'virial', 'direct_force', 'hessian')
 
 
 class NewtonNet(nn.Module):
@@ -97,7 +97,7 @@ class NewtonNet(nn.Module):
         for key in props:
             if key not in _SUPPORTED:
                 raise NotImplementedError(f"output '{key}' is outside the B200 energy/force/stress path")
-        if any(getattr(layer, 'create_graph', False) for layer in self.output_layers):
+        if 'hessian' in props or any(getattr(layer, 'create_graph', False) for layer in self.output_layers):
             from newtonnet_b200.train import differentiable_forward
             return differentiable_forward(self, z, pos, cell, batch)
         if not pos.is_cuda:

@@ -1,7 +1,7 @@
 """Output heads, scalers' companions and the result bag; mirrors newtonnet/models/output.py.
 
 Supported heads (the hot path of BASELINE.json): 'energy', 'gradient_force', 'stress', 'virial', plus
-'direct_force' (SURVEY.md section 8f rank 2).  'hessian', 'charge', 'bec' raise NotImplementedError
+'direct_force' and 'hessian' (SURVEY.md section 8f rank 2).  'charge', 'bec' raise NotImplementedError
 (out of scope; charge/bec need the un-vendored `les` package).
 
 The heads own parameters and flags only.  Energies, forces and virials are produced together by one
@@ -13,9 +13,9 @@ from torch import nn
 
 __all__ = ['get_output_by_string', 'get_aggregator_by_string', 'CustomOutputSet', 'DirectProperty',
            'DerivativeProperty', 'SecondDerivativeProperty', 'EnergyOutput', 'GradientForceOutput', 'DirectForceOutput',
-           'VirialOutput', 'StressOutput', 'EnergyAggregator', 'NullAggregator', 'SumAggregator']
+           'VirialOutput', 'StressOutput', 'HessianOutput', 'EnergyAggregator', 'NullAggregator', 'SumAggregator']
 
-_UNSUPPORTED = ('hessian', 'charge', 'bec')
+_UNSUPPORTED = ('charge', 'bec')
 
 
 def get_output_by_string(key, n_features=None, activation=None):
@@ -29,6 +29,8 @@ def get_output_by_string(key, n_features=None, activation=None):
         return VirialOutput()
     if key == 'stress':
         return StressOutput()
+    if key == 'hessian':
+        return HessianOutput()
     if key in _UNSUPPORTED:
         raise NotImplementedError(f"output '{key}' is outside the B200 energy/force/stress path")
     raise NotImplementedError(f'Output type {key} is not implemented yet')
@@ -37,7 +39,7 @@ def get_output_by_string(key, n_features=None, activation=None):
 def get_aggregator_by_string(key):
     if key == 'energy':
         return EnergyAggregator()
-    if key in ('gradient_force', 'direct_force', 'virial', 'stress'):
+    if key in ('gradient_force', 'direct_force', 'virial', 'stress', 'hessian'):
         return NullAggregator()
     if key in _UNSUPPORTED:
         raise NotImplementedError(f"output '{key}' is outside the B200 energy/force/stress path")
@@ -107,6 +109,11 @@ class DirectForceOutput(DirectProperty):
 
 class GradientForceOutput(DerivativeProperty):
     """force = -dE/dpos (models/output.py:109-113)."""
+
+
+class HessianOutput(SecondDerivativeProperty):
+    """hessian[i,a,j,b] = d^2 E / d pos_ia d pos_jb (models/output.py:134-152); evaluated on the differentiable
+    path (newtonnet_b200/train.py): one reverse pass through the force graph per row."""
 
 
 class VirialOutput(DerivativeProperty):

@@ -167,8 +167,8 @@ def differentiable_forward(model, z, pos, cell, batch):
     if 'energy' not in props:
         raise RuntimeError("output_properties must contain 'energy'")
     for key in props:
-        if key not in ('energy', 'gradient_force', 'direct_force'):
-            raise NotImplementedError(f"training-mode evaluation supports energy, gradient_force and direct_force, not '{key}'")
+        if key not in ('energy', 'gradient_force', 'direct_force', 'hessian'):
+            raise NotImplementedError(f"the differentiable path supports energy, gradient_force, direct_force and hessian, not '{key}'")
     if not pos.is_cuda:
         raise RuntimeError('newtonnet_b200: inputs must be CUDA tensors - there is no CPU fallback')
     if pos.dtype != torch.float32 or next(model.parameters()).dtype != torch.float32:
@@ -233,8 +233,19 @@ def differentiable_forward(model, z, pos, cell, batch):
             hd = Fn.silu(linear(a, dl[0].weight, dl[0].bias))
             hd = linear(Fn.silu(linear(hd, dl[2].weight, dl[2].bias)), dl[4].weight, dl[4].bias)
             out.direct_force = (hd.unsqueeze(1) * f.view(N, 3, F)).sum(-1) * ds.scale(z)
+        elif key == 'hessian':
+            # reference models/output.py:141-152 (vmap over unit vectors): one reverse pass per row of the 3N x 3N matrix
+            if not hasattr(out, 'pos_grad') or not out.pos_grad.requires_grad:
+                raise RuntimeError("'hessian' needs 'gradient_force' evaluated before it with create_graph=True "
+                                   "(MLAseCalculator sets this, reference utils/ase_interface.py:125-128)")
+            flat = out.pos_grad.reshape(-1)
+            keep = bool(model.output_layers[props.index(key)].create_graph)
+            rows = [torch.autograd.grad(flat[r], pos, retain_graph=True, create_graph=False)[0] for r in range(flat.numel())]
+            out.hessian = torch.stack(rows).reshape(N, 3, N, 3)
+            if not keep:
+                out.hessian = out.hessian.detach()
         else:
-            create = bool(model.output_layers[props.index(key)].create_graph)
+            create = bool(model.output_layers[props.index(key)].create_graph) or 'hessian' in props
             out.pos_grad, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=create,
                                                 retain_graph=create)
             out.gradient_force = -out.pos_grad

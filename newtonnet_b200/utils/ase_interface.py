@@ -82,7 +82,7 @@ class MLAseCalculator(_Calculator):
         n_frames, n_atoms = len(atoms), len(atoms[0])
         pred = self.model(z, pos, cell, batch)
         for key in self.properties:
-            if key in ('charges', 'bec', 'hessian'):
+            if key in ('charges', 'bec'):
                 raise NotImplementedError(f"property '{key}' is outside the B200 energy/force/stress path")
         if 'energy' in self.properties or 'free_energy' in self.properties:
             energy = pred.energy.cpu().detach().numpy()
@@ -93,6 +93,9 @@ class MLAseCalculator(_Calculator):
         if 'forces' in self.properties:
             force = pred.gradient_force.cpu().detach().numpy()
             self.results['forces'] = force.reshape(n_frames, n_atoms, 3).squeeze()
+        if 'hessian' in self.properties:
+            hessian = pred.hessian.cpu().detach().numpy()
+            self.results['hessian'] = hessian.reshape(n_frames, n_atoms, 3, n_atoms, 3).squeeze()
         if 'stress' in self.properties:
             stress = pred.stress.cpu().detach().numpy()
             self.results['stress'] = stress[:, [0, 1, 2, 1, 0, 0], [0, 1, 2, 2, 2, 1]].squeeze()   # Voigt

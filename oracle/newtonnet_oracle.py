@@ -399,6 +399,26 @@ def forward_analytic(sd, z, pos, cell, batch, dtype=torch.float64, cutoff=CUTOFF
     return out
 
 
+def hessian(sd, z, pos, cell, batch, dtype=torch.float64, cutoff=CUTOFF):
+    """HessianOutput, models/output.py:134-152: d(pos_grad)/d pos, [N,3,N,3]."""
+    sd = as_torch_sd(sd, dtype)
+    z = torch.as_tensor(np.asarray(z)).long()
+    batch = torch.as_tensor(np.asarray(batch)).long()
+    pos = torch.as_tensor(np.asarray(pos)).to(dtype).clone().requires_grad_(True)
+    cell = torch.as_tensor(np.asarray(cell)).to(dtype)
+    rbf, direction, edge_index = edge_embedding(sd, pos, cell, batch, cutoff)
+    a = sd['embedding_layers.node_embedding.weight'][z]
+    f = torch.zeros(z.shape[0], 3, a.shape[1], dtype=dtype)
+    for l in range(n_layers(sd)):
+        a, f = interaction(sd, l, a, f, direction, rbf, edge_index)
+    energy = _segment_sum(atomic_energy(sd, a, z), batch, cell.shape[0]).reshape(-1)
+    g, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=True)
+    flat = g.reshape(-1)
+    rows = [torch.autograd.grad(flat[r], pos, retain_graph=True)[0] for r in range(flat.numel())]
+    n = z.shape[0]
+    return torch.stack(rows).reshape(n, 3, n, 3).numpy()
+
+
 # ----------------------------------------------------------------------------- row T: training step
 def training_gradients(sd, z, pos, cell, batch, e_target, f_target, force_weight=50.0, dtype=torch.float64,
                        cutoff=CUTOFF):

@@ -353,8 +353,28 @@ def widening_golden():
               f'|DF|max {np.abs(d["ref64_direct_force"]).max():.3f} 32-vs-64 dF {np.abs(d["ref32_forces"]-d["ref64_forces"]).max():.2e}')
 
 
+def hessian_golden():
+    """HessianOutput (models/output.py:134-152) of one aspirin frame with the shipped weights, fp64."""
+    sd = dict(np.load(f'{OUT}/weights_md17.npz'))
+    kat = np.load(f'{OUT}/md17_kat.npz')
+    z = torch.tensor(kat['numbers']); p = torch.tensor(kat['positions'][0], dtype=torch.float64)
+    m = NewtonNet(output_properties=['energy', 'gradient_force', 'hessian'])
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+    m = m.double(); m.eval()
+    for layer in m.output_layers:                      # what MLAseCalculator.load_model does (ase_interface.py:125-128)
+        if hasattr(layer, 'create_graph'):
+            layer.create_graph = True
+    out = m(z, p.clone(), torch.zeros(1, 3, 3, dtype=torch.float64), torch.zeros(21, dtype=torch.long))
+    h = out.hessian.detach().numpy()
+    np.savez_compressed(f'{OUT}/hessian_aspirin1.npz', z=z.numpy(), pos=p.numpy().astype(np.float32), hessian=h,
+                        forces=out.gradient_force.detach().numpy())
+    print('hessian', h.shape, np.abs(h).max(), 'asym', np.abs(h.reshape(63, 63) - h.reshape(63, 63).T).max())
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'wide':
+    if len(sys.argv) > 1 and sys.argv[1] == 'hessian':
+        hessian_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'wide':
         widening_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == 'train':
         training_golden()
@@ -362,3 +382,4 @@ if __name__ == '__main__':
         main()
         training_golden()
         widening_golden()
+        hessian_golden()

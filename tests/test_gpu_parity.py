@@ -487,3 +487,19 @@ def test_ase_calculator(tmp_path):
     assert calc.results['stress'].shape == (6,)
     assert np.abs(calc.results['stress'] - voigt).max() < 1e-4 * np.abs(voigt).max()
     assert np.abs(calc.results['forces'] - d['ref64_forces']).max() < F_ATOL
+
+
+def test_hessian_through_the_calculator(tmp_path):
+    """hessian head via MLAseCalculator, against the unmodified reference (fp64 golden)."""
+    from newtonnet_b200.compat import model_from_state_dict
+    from newtonnet_b200.utils.ase_interface import MLAseCalculator
+    d = np.load(f'{GOLDEN}/hessian_aspirin1.npz')
+    w = load_weights('md17')
+    path = tmp_path / 'm.pt'
+    torch.save(model_from_state_dict({k: torch.tensor(v) for k, v in w.items()}), path)
+    calc = MLAseCalculator(str(path), properties=['energy', 'forces', 'hessian'], device='cuda:0')
+    calc.calculate(FakeAtoms(d['z'], d['pos']))
+    h = calc.results['hessian']
+    assert h.shape == (21, 3, 21, 3)
+    assert np.abs(h - d['hessian']).max() < 2e-3 and np.abs(d['hessian']).max() > 50
+    assert np.abs(calc.results['forces'] - d['forces']).max() < F_ATOL

@@ -66,7 +66,7 @@ def test_factories_and_unsupported_heads():
     assert get_scaler_by_string('energy').scale is not None and get_scaler_by_string('stress').scale is None
     for key in ('gradient_force', 'stress', 'virial'):
         get_output_by_string(key); get_aggregator_by_string(key)
-    for key in ('charge', 'hessian', 'bec'):
+    for key in ('charge', 'bec'):
         with pytest.raises(NotImplementedError):
             get_output_by_string(key, 128, torch.nn.SiLU())
     assert len(list(get_output_by_string('direct_force', 128, torch.nn.SiLU()).parameters())) == 6

@@ -126,3 +126,11 @@ def test_layer_norm_and_direct_force_match_reference(name):
     np.testing.assert_allclose(o['energy'], d['ref64_energy'], rtol=1e-12, atol=1e-10)
     assert np.abs(o['forces'] - d['ref64_forces']).max() < 1e-12
     assert np.abs(o['direct_force'] - d['ref64_direct_force']).max() < 1e-12
+
+
+def test_hessian_matches_reference():
+    d = np.load(f'{GOLDEN}/hessian_aspirin1.npz')
+    w = load_weights('md17')
+    h = O.hessian(w, d['z'], d['pos'], np.zeros((1, 3, 3)), np.zeros(21, dtype=np.int64))
+    assert h.shape == (21, 3, 21, 3)
+    assert np.abs(h - d['hessian']).max() < 1e-4        # golden positions are stored in fp32
