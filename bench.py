@@ -336,6 +336,26 @@ def main_b200(args):
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_s / K * 1e3,
                'api': api}
 
+    # ---- device-resident MD (caller side): same box, integrator state in HBM, one CUDA graph per step
+    md_info = None
+    if args.workload in ('c1', 'c3') and world == 1 and not args.no_e2e:
+        try:
+            from newtonnet_b200.md import DeviceMD, FS
+            md = DeviceMD(model, z_h, steps_pos[0].astype(np.float64), cell=cell_h, batch=batch_h, temperature_K=300.0,
+                          friction=1.0 / (500 * FS), timestep=0.5 * FS, check_interval=max(K, 1))
+            md.run(max(W, 3))
+            n_md = max(K, 20)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            md.run(n_md)                                           # ends with the status / log read (synchronises)
+            md_s = time.perf_counter() - t0
+            md_info = {'ms_per_step': md_s / n_md * 1e3, 'value': N * n_md / md_s, 'unit': UNIT, 'steps': n_md,
+                       'kernels_per_step': md.kernels_per_step, 'graph_replays': n_md,
+                       'what': 'newtonnet_b200.md.DeviceMD.run: Langevin (BAOAB) step + neighbour rebuild + energy/forces, state '
+                               'resident in HBM, wall clock including the per-chunk status/log read; no stress'}
+        except RuntimeError as exc:      # random-weight potential energy surfaces can collapse a box; report, do not fail the bench
+            md_info = {'error': str(exc)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,6 +433,8 @@ def main_b200(args):
         'gpu_launches': launches, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'cpu_baseline': cpu_base,
         'stages': table,
     }
+    if md_info:
+        line['md_device_resident'] = md_info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -290,6 +290,22 @@ NN_API int nn_segment_sum(const float* src, const int32_t* perm, const int32_t* 
 NN_API size_t nn_gemm128_tn_workspace_bytes(int32_t m);
 NN_API int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream);
 
+/* ---- device-resident molecular dynamics (caller side of the path) --------------------
+ * Replaces the per-step host loop of the reference's MD driver: scripts/simulate.py:21-31 (ASE Langevin) calling
+ * MLAseCalculator.calculate, utils/ase_interface.py:52-81, i.e. numpy -> H2D -> forward -> D2H every step.
+ * One step = nn_md_advance -> nn_nbr_count -> nn_nbr_fill -> nn_eval -> nn_md_finish on one stream (CUDA graph
+ * capturable: every step-dependent quantity, including the step counter, lives in device memory).
+ * BAOAB splitting; ou_c = exp(-friction * dt) (1.0 = velocity Verlet, no noise), kT in the energy unit.
+ * x, v: [n_atoms,3] fp64 state (x unwrapped); pos_model: [n_atoms,3] fp32 wrapped positions bound to nn_nbr.pos. */
+NN_API int nn_md_advance(int32_t n_atoms, double* x, double* v, const float* force, const double* inv_mass, const float* cell,
+                         const int64_t* batch, float* pos_model, double dt, double ou_c, double kT, uint64_t seed,
+                         const int64_t* step_ctr, void* stream);
+/* second half kick with the new forces; writes log[(step % log_cap), system, {potential, kinetic}] (fp64), ORs the
+ * neighbour-list status words into sticky[0..2] = {edges needed, max degree, singular cell} and increments *step_ctr. */
+NN_API int nn_md_finish(int32_t n_systems, const int32_t* sys_ptr, double* v, const float* force, const double* inv_mass,
+                        double dt, const float* energy, double* log, int32_t log_cap, int64_t* step_ctr,
+                        const int32_t* nbr_status, int32_t* sticky, uint32_t* ticket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

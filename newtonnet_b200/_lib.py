@@ -92,6 +92,8 @@ SYMBOLS = {
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    'nn_md_advance': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_double, C.c_double, C.c_uint64, _fp, _fp]),
+    'nn_md_finish': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_double, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_bwd': (C.c_int, [_fp, C.c_int32, _fp, _fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp]),
     'nn_message_prepare_b': (C.c_int, [_fp, _fp, _fp]),
