@@ -24,6 +24,9 @@ constexpr int MMA_WARP = PRODUCER_WARPS + EPI_WARPS;
 constexpr int THREADS = 32 * 16;
 constexpr uint32_t B_BYTES = 2 * BLK_BYTES;            // We image: hi + lo, one K block
 constexpr uint32_t BAR_BYTES = 256;
+// 512 threads x 128 registers at launch; after setmaxnreg: 4 warps x 104 (producers) + 4 x 40 (MMA warpgroup) + 8 x 184
+// (epilogue) = 2048 = 16 x 128
+constexpr int REGS_PROD = 104, REGS_MMA = 40, REGS_EPI = 184;
 
 template <bool BWD> struct Cfg {
     static constexpr int NA = BWD ? 2 : 1;              // A operands per tile (rbf [, drbf])
@@ -84,7 +87,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
+    // register files: producers and the MMA warpgroup hand registers to the two epilogue warpgroups
     if (warp < PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
         // ===================== producers: rbf rows (80 B) -> zero-padded 128 B swizzle rows, hi / lo =====================
         const int r4 = lane >> 3, chunk = lane & 7;
         const int my_tiles = has_work ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -129,8 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
                 if (w + PF < my_tiles) issue(w + PF, v[u]);
             }
         }
-    } else if (warp == MMA_WARP) {
-        if (lane == 0 && has_work) {
+    } else if (warp >= MMA_WARP) {                      // warpgroup 3: the MMA warp and three idle warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+        if (warp == MMA_WARP && lane == 0 && has_work) {
             mbar_expect_tx(bar_b_full, B_BYTES);
             bulk_g2s(sB, a.B_img, BLK_BYTES, bar_b_full);
             bulk_g2s(sB + BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + BLK_BYTES, BLK_BYTES, bar_b_full);
@@ -162,25 +168,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
             }
         }
         __syncwarp();
-    } else if (warp < MMA_WARP) {
+    } else {
         // ===================== epilogue =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        // The gathers (mn_i, mn_j [, abar_i, abar_j, mbar_p]) are L2 / HBM latency chains; each warp keeps a rolling
+        // window of two row groups in flight (registers handed over by the producer / MMA warpgroups, setmaxnreg),
+        // running across chunk and tile boundaries - the addresses depend on the pair list only, not on the MMA.
         const int q = warp & 3, ew = warp - PRODUCER_WARPS, half = ew >> 2;
         const int r4 = lane >> 3, c8 = lane & 7;
         uint8_t* stg = smem_gen + (sStg - base) + ew * STG_BYTES;
+        constexpr int G = C::G, NG = 8 / G, NL = BWD ? 5 : 2;
+        float4 win[2][G][NL];
+        // pair endpoints of this warp's 32 rows: lane l holds row l (current tile and the next one)
+        int cur_i = 0, cur_j = 0, nxt_i = 0, nxt_j = 0;
+        auto load_idx = [&](int tile, int& oi, int& oj) {
+            const int p = tile * TM + q * 32 + lane;
+            const bool ok = tile < n_tiles && p < M;
+            oi = ok ? a.pair_i[p] : 0;
+            oj = ok ? a.pair_j[p] : 0;
+        };
+        auto issue = [&](int tile, int vi, int vj, int c, int g, float4 (&dst)[G][NL]) {
+            const int col = half * 64 + c * 32 + 4 * c8;
+#pragma unroll
+            for (int kk = 0; kk < G; ++kk) {
+                const int row = (g * G + kk) * 4 + r4;
+                const int ii = __shfl_sync(0xffffffffu, vi, row), jj = __shfl_sync(0xffffffffu, vj, row);
+                const int p = tile * TM + q * 32 + row;
+                if (p < M) {
+                    dst[kk][0] = ld4(a.mn + (size_t)ii * kF + col);
+                    dst[kk][1] = ld4(a.mn + (size_t)jj * kF + col);
+                    if (BWD) {
+                        dst[kk][2] = ld4(a.abar + (size_t)ii * kF + col);
+                        dst[kk][3] = ld4(a.abar + (size_t)jj * kF + col);
+                        dst[kk][NL - 1] = ld4(a.io + (size_t)p * kF + col);
+                    }
+                }
+            }
+        };
+        if (has_work) {
+            load_idx(blockIdx.x, cur_i, cur_j);
+            issue(blockIdx.x, cur_i, cur_j, 0, 0, win[0]);
+        }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
             const int prow0 = tile * TM + q * 32;
-            // pair endpoints of this lane's 8 rows (row = k*4 + r4); issued before the accumulator is awaited
-            int pi[BWD ? 1 : 8], pj[BWD ? 1 : 8];
-            if (!BWD) {
-#pragma unroll
-                for (int k = 0; k < (BWD ? 1 : 8); ++k) {
-                    const int p = prow0 + k * 4 + r4;
-                    pi[k] = p < M ? a.pair_i[p] : 0;
-                    pj[k] = p < M ? a.pair_j[p] : 0;
-                }
-            }
+            const int next_tile = tile + (int)gridDim.x;
+            load_idx(next_tile, nxt_i, nxt_j);
             mbar_wait(bar_t_full + 8 * buf, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS;
@@ -191,36 +225,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
             for (int c = 0; c < 2; ++c) {
                 const int c0 = half * 64 + c * 32;
                 const int col = c0 + 4 * c8;
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
+                {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
                 __syncwarp();
-                float4 y[8];
-                constexpr int G = C::G;
+                float4 y[BWD ? 8 : 1];
 #pragma unroll
-                for (int g = 0; g < 8 / G; ++g) {      // G rows at a time: 2 (fwd) or 5 (bwd) gathers per row in flight
-                    float4 gi[G], gj[G], ai[G], aj[G], mb[G];
-#pragma unroll
-                    for (int kk = 0; kk < G; ++kk) {
-                        const int k = g * G + kk;
-                        const int p = prow0 + k * 4 + r4;
-                        if (p < M) {
-                            const int ii = BWD ? a.pair_i[p] : pi[BWD ? 0 : k];
-                            const int jj = BWD ? a.pair_j[p] : pj[BWD ? 0 : k];
-                            gi[kk] = ld4(a.mn + (size_t)ii * kF + col);
-                            gj[kk] = ld4(a.mn + (size_t)jj * kF + col);
-                            if (BWD) {
-                                ai[kk] = ld4(a.abar + (size_t)ii * kF + col);
-                                aj[kk] = ld4(a.abar + (size_t)jj * kF + col);
-                                mb[kk] = ld4(a.io + (size_t)p * kF + col);
-                            }
-                        }
-                    }
+                for (int g = 0; g < NG; ++g) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int n = c * NG + g;                           // static after unrolling; 2 * NG is even
+                    if (g + 1 < NG) issue(tile, cur_i, cur_j, c, g + 1, win[(n + 1) & 1]);
+                    else if (c == 0) issue(tile, cur_i, cur_j, 1, 0, win[(n + 1) & 1]);
+                    else if (next_tile < n_tiles) issue(next_tile, nxt_i, nxt_j, 0, 0, win[(n + 1) & 1]);
+                    float4 (&w)[G][NL] = win[n & 1];
 #pragma unroll
                     for (int kk = 0; kk < G; ++kk) {
                         const int k = g * G + kk;
@@ -228,21 +252,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
                         const int p = prow0 + row;
                         const float4 me = *reinterpret_cast<const float4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4));
                         if (p < M) {
-                            const float4 prod = f4_mul(gi[kk], gj[kk]);
+                            const float4 prod = f4_mul(w[kk][0], w[kk][1]);
                             if (!BWD) {
                                 st4(a.io + (size_t)p * kF + col, f4_mul(me, prod));
                             } else {
-                                const float4 mt = f4_add(mb[kk], f4_add(ai[kk], aj[kk]));
-                                y[k] = f4_mul(mt, prod);
+                                const float4 mt = f4_add(w[kk][NL - 1], f4_add(w[kk][2], w[kk][3]));
+                                y[BWD ? k : 0] = f4_mul(mt, prod);
                                 st4(a.io + (size_t)p * kF + col, f4_mul(mt, me));
                             }
                         } else if (BWD) {
-                            y[k] = f4_zero();
+                            y[BWD ? k : 0] = f4_zero();
                         }
                     }
                 }
                 __syncwarp();
                 if (BWD) {                              // second accumulator: dme = We drbf_p
+                    uint32_t v[32];
                     tmem_ld32(taddr + 128 + c0, v);
                     tmem_ld_wait();
 #pragma unroll
@@ -255,7 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
                     for (int k = 0; k < 8; ++k) {
                         const int row = k * 4 + r4;
                         const float4 dme = *reinterpret_cast<const float4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4));
-                        xs[k] += f4_dot(y[k], dme);
+                        xs[k] += f4_dot(y[BWD ? k : 0], dme);
                     }
                     __syncwarp();
                 }
@@ -275,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
                     if (c8 == 0 && p < M) a.x_part[(size_t)half * a.cap + p] = s;
                 }
             }
+            cur_i = nxt_i; cur_j = nxt_j;
         }
     }
     tc_fence_before();
