@@ -35,7 +35,14 @@ template <bool BWD> struct Cfg {
     static constexpr uint32_t TMEM_COLS = BWD ? 512 : 256;
     static constexpr uint32_t ACC_COLS = BWD ? 256 : 128;   // columns per accumulator buffer
     static constexpr int PF = BWD ? 1 : 2;              // tiles of rbf rows in flight in registers per producer thread
-    static constexpr int G = BWD ? 2 : 4;               // rows per lane whose gathers are in flight together
+#ifndef NN_MSG_FWD_G
+#define NN_MSG_FWD_G 4
+#define NN_MSG_FWD_D 2
+#define NN_MSG_BWD_G 2
+#define NN_MSG_BWD_D 2
+#endif
+    static constexpr int G = BWD ? NN_MSG_BWD_G : NN_MSG_FWD_G;   // rows per lane in one gather group
+    static constexpr int D = BWD ? NN_MSG_BWD_D : NN_MSG_FWD_D;   // window depth: D - 1 groups in flight behind the one being consumed
 };
 
 struct MsgArgs {
@@ -177,8 +184,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
         const int q = warp & 3, ew = warp - PRODUCER_WARPS, half = ew >> 2;
         const int r4 = lane >> 3, c8 = lane & 7;
         uint8_t* stg = smem_gen + (sStg - base) + ew * STG_BYTES;
-        constexpr int G = C::G, NG = 8 / G, NL = BWD ? 5 : 2;
-        float4 win[2][G][NL];
+        constexpr int G = C::G, NG = 8 / G, NL = BWD ? 5 : 2, D = C::D, GT = 2 * NG;   // GT groups per tile
+        static_assert(GT % D == 0, "window slots must line up across tiles");
+        float4 win[D][G][NL];
         // pair endpoints of this warp's 32 rows: lane l holds row l (current tile and the next one)
         int cur_i = 0, cur_j = 0, nxt_i = 0, nxt_j = 0;
         auto load_idx = [&](int tile, int& oi, int& oj) {
@@ -207,7 +215,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
         };
         if (has_work) {
             load_idx(blockIdx.x, cur_i, cur_j);
-            issue(blockIdx.x, cur_i, cur_j, 0, 0, win[0]);
+#pragma unroll
+            for (int m = 0; m < D - 1; ++m) issue(blockIdx.x, cur_i, cur_j, m / NG, m % NG, win[m]);
         }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -239,12 +248,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
                 float4 y[BWD ? 8 : 1];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int n = c * NG + g;                           // static after unrolling; 2 * NG is even
-                    if (g + 1 < NG) issue(tile, cur_i, cur_j, c, g + 1, win[(n + 1) & 1]);
-                    else if (c == 0) issue(tile, cur_i, cur_j, 1, 0, win[(n + 1) & 1]);
-                    else if (next_tile < n_tiles) issue(next_tile, nxt_i, nxt_j, 0, 0, win[(n + 1) & 1]);
-                    float4 (&w)[G][NL] = win[n & 1];
+                    const int n = c * NG + g, m = n + D - 1;            // static after unrolling; consume n, issue m
+                    if (m < GT) issue(tile, cur_i, cur_j, m / NG, m % NG, win[m % D]);
+                    else if (next_tile < n_tiles) issue(next_tile, nxt_i, nxt_j, (m - GT) / NG, (m - GT) % NG, win[m % D]);
+                    float4 (&w)[G][NL] = win[n % D];
 #pragma unroll
                     for (int kk = 0; kk < G; ++kk) {
                         const int k = g * G + kk;

@@ -38,26 +38,38 @@ __device__ __forceinline__ float envelope_grad(float x) {
     return -495.f * x4 * x4 * t * t;
 }
 
-__global__ void k_edge_geom_fwd(const float* __restrict__ disp, const float* __restrict__ freq, float cutoff,
-                                const int* __restrict__ n_dev, int cap, float* __restrict__ rbf,
-                                float* __restrict__ drbf, float* __restrict__ unit, float* __restrict__ dist) {
+// Five lanes per pair, four basis functions each: every lane stores one float4 of the pair's 80-byte rbf / drbf rows,
+// so a warp's stores cover consecutive 16-byte pieces (a thread-per-pair loop writes 32 different rows per instruction).
+__global__ void __launch_bounds__(320)
+k_edge_geom_fwd(const float* __restrict__ disp, const float* __restrict__ freq, float cutoff,
+                const int* __restrict__ n_dev, int cap, float* __restrict__ rbf,
+                float* __restrict__ drbf, float* __restrict__ unit, float* __restrict__ dist) {
+    static_assert(kNB == 20, "five float4 per basis row");
     const int P = dev_count(n_dev, cap);
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const long long total = (long long)P * 5;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(t / 5), quad = (int)(t - (long long)p * 5);
         float3 d3 = make_float3(disp[3 * p], disp[3 * p + 1], disp[3 * p + 2]);
         float d = nn_norm3(d3);
-        unit[3 * p] = __fdiv_rn(d3.x, d); unit[3 * p + 1] = __fdiv_rn(d3.y, d); unit[3 * p + 2] = __fdiv_rn(d3.z, d);
-        dist[p] = d;
+        if (quad == 0) {
+            unit[3 * p] = __fdiv_rn(d3.x, d); unit[3 * p + 1] = __fdiv_rn(d3.y, d); unit[3 * p + 2] = __fdiv_rn(d3.z, d);
+            dist[p] = d;
+        }
         float x = __fdiv_rn(d, cutoff);
         float env = envelope(x), envp = envelope_grad(x), invx = 1.0f / x;
+        const float fr[4] = {freq[4 * quad], freq[4 * quad + 1], freq[4 * quad + 2], freq[4 * quad + 3]};
+        float r[4], dr[4];
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) {
-            float fx = freq[n] * x, sn, cs;
+        for (int n = 0; n < 4; ++n) {
+            float fx = fr[n] * x, sn, cs;
             sincosf(fx, &sn, &cs);
             float sb = sn * invx;
-            rbf[(size_t)p * kNB + n] = env * sb;
+            r[n] = env * sb;
             // d/dx [env(x) sin(f x)/x] = env' sb + env (f x cos(f x) - sin(f x)) / x^2
-            if (drbf) drbf[(size_t)p * kNB + n] = fmaf(envp, sb, env * (fx * cs - sn) * invx * invx);
+            dr[n] = fmaf(envp, sb, env * (fx * cs - sn) * invx * invx);
         }
+        st4(rbf + (size_t)p * kNB + 4 * quad, make_float4(r[0], r[1], r[2], r[3]));
+        if (drbf) st4(drbf + (size_t)p * kNB + 4 * quad, make_float4(dr[0], dr[1], dr[2], dr[3]));
     }
 }
 
@@ -596,8 +608,8 @@ int grid_for_rows(long long rows) {
 extern "C" int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
                                 int32_t cap_pairs, float* rbf, float* drbf, float* unit, float* dist, void* stream) {
     if (cap_pairs <= 0) return 0;
-    int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
-    k_edge_geom_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, drbf, unit, dist); NN_LAUNCHED(1);
+    int grid = min(nn_ceil_div((long long)cap_pairs * 5, 320), 148 * 6);
+    k_edge_geom_fwd<<<grid, 320, 0, (cudaStream_t)stream>>>(pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, drbf, unit, dist); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_fwd");
     return 0;
 }
