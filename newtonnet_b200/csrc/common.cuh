@@ -10,6 +10,7 @@ static constexpr int kF = NN_F;      // 128 features: one warp covers a row with
 static constexpr int kNB = NN_NB;    // 20 radial basis functions
 
 void nn_set_error(const char* fmt, ...);
+bool nn_pdl_enabled();     // programmatic dependent launch of the tensor-core kernels (NN_PDL=0 turns it off)
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 void nn_count_launches(int n);
 // optional per-stage CUDA-event profiler (nn_profile_enable): stages are timed on the launching stream
@@ -33,6 +34,9 @@ struct ProfScope {
         }                                                                           \
     } while (0)
 #define NN_LAUNCHED(n) nn_count_launches(n)
+// first statement of a kernel whose successor may be a PDL kernel (tc_common.cuh): lets that kernel's prologue start
+// as soon as every CTA of this grid is resident; it still waits for this grid to complete before reading its results
+#define NN_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
 #define NN_REQUIRE(cond, msg)                                                       \
     do {                                                                            \

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // nn_eval: one call = one NewtonNet energy (+ forces, virial, stress) evaluation on a prebuilt
 // neighbour list.  Launches the staged kernels on one stream, no host synchronisation, all buffers
 // carved from the caller's workspace; capturable in a CUDA graph.
@@ -43,6 +44,12 @@ extern "C" int nn_version(void) { return 100; }
 #include <vector>
 static std::atomic<long long> g_launches{0};
 void nn_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool nn_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 extern "C" long long nn_launch_count(int reset) {
     long long v = g_launches.load();
     if (reset) g_launches.store(0);

@@ -87,17 +87,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));           // generic pointer to `base`
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int M = a.m;
-    if (a.m_dev) { long long v = (long long)a.m_dev[0] * a.m_dev_mul; M = v < a.m ? (int)v : a.m; }
-    const int n_tiles = (M + TM - 1) / TM;
-    const bool has_work = (int)blockIdx.x < n_tiles;
 
+    // Programmatic dependent launch: everything up to pdl_wait() touches only this kernel's constants (barriers,
+    // tensor memory, the weight image), so it overlaps the tail of the preceding kernel in the stream.
+    pdl_launch_dependents();
     if (warp == MMA_WARP) {
         if (lane == 0) {
             mbar_init(bar_b_full, 1);
             for (int s = 0; s < NKB; ++s) { mbar_init(bar_a_full + 8 * s, 4 * 32); mbar_init(bar_a_empty + 8 * s, 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full + 8 * b, 1); mbar_init(bar_t_empty + 8 * b, EPI_WARPS * 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar_b_full, B_BYTES);
+            for (int c = 0; c < (int)(B_BYTES / BLK_BYTES); ++c)
+                bulk_g2s(sB + c * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + (size_t)c * BLK_BYTES, BLK_BYTES, bar_b_full);
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
@@ -107,6 +109,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+    pdl_wait();                                       // results of the preceding kernels are visible from here on
+    int M = a.m;
+    if (a.m_dev) { long long v = (long long)a.m_dev[0] * a.m_dev_mul; M = v < a.m ? (int)v : a.m; }
+    const int n_tiles = (M + TM - 1) / TM;
+    const bool has_work = (int)blockIdx.x < n_tiles;
 
     if (warp < PRODUCER_WARPS) {
         // ===================== producers: X rows -> transpose -> hi/lo split -> TMEM =====================
@@ -179,11 +186,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == MMA_WARP) {
         // ===================== B load + MMA issue (one elected lane) =====================
+        if (lane == 0) mbar_wait(bar_b_full, 0);           // the image copy must have landed before the CTA may exit
         if (lane == 0 && has_work) {
-            mbar_expect_tx(bar_b_full, B_BYTES);
-            for (int c = 0; c < (int)(B_BYTES / BLK_BYTES); ++c)
-                bulk_g2s(sB + c * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + (size_t)c * BLK_BYTES, BLK_BYTES, bar_b_full);
-            mbar_wait(bar_b_full, 0);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
@@ -308,8 +312,8 @@ int launch(const nn_gemm_args& a, cudaStream_t s) {
     }
     int tiles = nn_ceil_div(a.m, TM);
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    k_gemm128_ts<PRO, EPI><<<grid, THREADS, SMEM_BYTES, s>>>(a); NN_LAUNCHED(1);
-    return 0;
+    NN_LAUNCHED(1);
+    return launch_pdl(k_gemm128_ts<PRO, EPI>, grid, THREADS, SMEM_BYTES, s, a);
 }
 
 }  // namespace

@@ -73,17 +73,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int M = a.cap;
-    if (a.n_dev) { int v = a.n_dev[0]; M = v < a.cap ? v : a.cap; }
-    const int n_tiles = (M + TM - 1) / TM;
-    const bool has_work = (int)blockIdx.x < n_tiles;
 
+    pdl_launch_dependents();                          // see gemm_ts.cu: the prologue overlaps the preceding kernel's tail
     if (warp == MMA_WARP) {
         if (lane == 0) {
             mbar_init(bar_b_full, 1);
             for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a_full + 8 * s, PRODUCER_WARPS * 32); mbar_init(bar_a_empty + 8 * s, 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full + 8 * b, 1); mbar_init(bar_t_empty + 8 * b, EPI_WARPS * 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar_b_full, B_BYTES);
+            bulk_g2s(sB, a.B_img, BLK_BYTES, bar_b_full);
+            bulk_g2s(sB + BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + BLK_BYTES, BLK_BYTES, bar_b_full);
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
@@ -93,6 +93,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+    pdl_wait();
+    int M = a.cap;
+    if (a.n_dev) { int v = a.n_dev[0]; M = v < a.cap ? v : a.cap; }
+    const int n_tiles = (M + TM - 1) / TM;
+    const bool has_work = (int)blockIdx.x < n_tiles;
 
     // register files: producers and the MMA warpgroup hand registers to the two epilogue warpgroups
     if (warp < PRODUCER_WARPS) {
@@ -143,11 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_message_tc(MsgArgs a) {
         }
     } else if (warp >= MMA_WARP) {                      // warpgroup 3: the MMA warp and three idle warps
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+        if (warp == MMA_WARP && lane == 0) mbar_wait(bar_b_full, 0);
         if (warp == MMA_WARP && lane == 0 && has_work) {
-            mbar_expect_tx(bar_b_full, B_BYTES);
-            bulk_g2s(sB, a.B_img, BLK_BYTES, bar_b_full);
-            bulk_g2s(sB + BLK_BYTES, reinterpret_cast<const uint8_t*>(a.B_img) + BLK_BYTES, BLK_BYTES, bar_b_full);
-            mbar_wait(bar_b_full, 0);
             uint32_t stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
@@ -348,8 +350,8 @@ int launch(const MsgArgs& a, cudaStream_t s) {
     }
     int tiles = nn_ceil_div(a.cap, TM);
     int grid = tiles < g_sms ? tiles : g_sms;
-    k_message_tc<BWD><<<grid, THREADS, C::SMEM, s>>>(a); NN_LAUNCHED(1);
-    return 0;
+    NN_LAUNCHED(1);
+    return launch_pdl(k_message_tc<BWD>, grid, THREADS, C::SMEM, s, a);
 }
 
 }  // namespace

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(320)
 k_edge_geom_fwd(const float* __restrict__ disp, const float* __restrict__ freq, float cutoff,
                 const int* __restrict__ n_dev, int cap, float* __restrict__ rbf,
                 float* __restrict__ drbf, float* __restrict__ unit, float* __restrict__ dist) {
+    NN_PDL_TRIGGER();
     static_assert(kNB == 20, "five float4 per basis row");
     const int P = dev_count(n_dev, cap);
     const long long total = (long long)P * 5;
@@ -155,6 +156,7 @@ k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row
                      const int* __restrict__ edge_pair, int N, const float* __restrict__ msg, const float* __restrict__ e1,
                      const float* __restrict__ e2, const float* __restrict__ unit, const float* __restrict__ a_in,
                      const float* __restrict__ f_in, float* __restrict__ a_out, float* __restrict__ f_out) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;   // overflow: row_ptr is ahead of col / edge_pair
@@ -199,6 +201,7 @@ k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row
 
 __global__ void k_equiv_update_fwd(const float* __restrict__ a_in, const float* __restrict__ f,
                                    const float* __restrict__ g, float* __restrict__ a_out, int N) {
+    NN_PDL_TRIGGER();
     int t = blockIdx.x * blockDim.x + threadIdx.x;       // one float4 of one atom
     if (t >= N * (kF / 4)) return;
     int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
@@ -213,6 +216,7 @@ __global__ void k_equiv_update_fwd(const float* __restrict__ a_in, const float* 
 
 __global__ void k_embed(const int64_t* __restrict__ z, const float* __restrict__ emb, float* __restrict__ a, int N,
                         int* __restrict__ status) {
+    NN_PDL_TRIGGER();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * (kF / 4)) return;
     int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
@@ -226,6 +230,7 @@ __global__ void k_embed(const int64_t* __restrict__ z, const float* __restrict__
 __global__ void __launch_bounds__(kThreads)
 k_layer_norm_fwd(float* __restrict__ a_io, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float* __restrict__ xhat, float* __restrict__ rstd, int n_rows) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= n_rows) return;
@@ -243,6 +248,7 @@ k_layer_norm_fwd(float* __restrict__ a_io, const float* __restrict__ gamma, cons
 __global__ void __launch_bounds__(kThreads)
 k_layer_norm_bwd(float* __restrict__ abar_io, const float* __restrict__ gamma, const float* __restrict__ xhat,
                  const float* __restrict__ rstd, int n_rows) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= n_rows) return;
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(kThreads)
 k_energy_atom(const float* __restrict__ h2pre, const float* __restrict__ w3, const float* __restrict__ b3,
               const float* __restrict__ scale, const float* __restrict__ shift, const int64_t* __restrict__ z,
               int N, float* __restrict__ e_atom) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= N) return;
@@ -310,6 +317,7 @@ __global__ void k_energy_sum(const float* __restrict__ e_atom, const int* __rest
 __global__ void k_energy_head_seed(const float* __restrict__ h2pre, const float* __restrict__ w3,
                                    const float* __restrict__ scale, const int64_t* __restrict__ z, int N,
                                    float* __restrict__ gh2) {
+    NN_PDL_TRIGGER();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * (kF / 4)) return;
     int i = t / (kF / 4), q = (t % (kF / 4)) * 4;
@@ -329,6 +337,7 @@ k_pair_bwd_gather(const int* __restrict__ pair_ptr, const int* __restrict__ pair
                   const float* __restrict__ dfb, const float* __restrict__ f_in,
                   const float* __restrict__ unit, float* __restrict__ e1_io, float* __restrict__ e2bar,
                   float* __restrict__ ubar) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     for (int i = blockIdx.x * kWarps + (threadIdx.x >> 5); i < N; i += gridDim.x * kWarps) {
         const int p0 = pair_ptr[i], p1 = min(pair_ptr[i + 1], cap);
@@ -447,6 +456,7 @@ __global__ void __launch_bounds__(kThreads)
 k_node_aggregate_bwd(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
                      const int* __restrict__ edge_pair, int N, const float* __restrict__ t, const float* __restrict__ mn, const float* __restrict__ e2,
                      const float* __restrict__ dfb, float* __restrict__ mnbar, float* __restrict__ fbar_new) {
+    NN_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (k >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;

@@ -113,5 +113,25 @@ __device__ __forceinline__ float tf32_hi(float x) {
     return __uint_as_float(u);
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// griddepcontrol.launch_dependents: the next kernel in the stream (if it was launched with the programmatic
+// stream serialization attribute) may start once every CTA of this grid has passed this point or exited.
+// griddepcontrol.wait: blocks until all prerequisite grids have COMPLETED and their memory is visible - the
+// dependent kernel may only touch its own constants before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Kernel, typename Args>
+inline int launch_pdl(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t s, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = nn_pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args);
+    if (e != cudaSuccess) { nn_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
 
 }  // namespace tc
