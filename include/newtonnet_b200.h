@@ -172,6 +172,27 @@ typedef struct {
     int32_t prologue, epilogue;
 } nn_gemm_args;
 NN_API int nn_gemm128(const nn_gemm_args* a, void* stream);
+/* Two chained contractions in one kernel (a cluster of two CTAs, the intermediate tile travels through distributed
+ * shared memory instead of HBM):  Y = out( mid(X . B1) . B2 ).  Every two-layer 128->128 MLP of the path and its
+ * reverse: models/newtonnet.py:181-199 (message_nodepart, equiv_message1/2), models/output.py:90-96 (energy head).
+ *   mid = NN_MID_SILU_SAVE: q = acc + bias1; aux_out = silu'(q); h = silu(q)      (forward)
+ *   mid = NN_MID_MUL      : h = acc * aux1                                         (reverse)
+ *   out = NN_OUT_BIAS     : Y = acc + bias2 (bias2 may be NULL)     out = NN_OUT_ADD: Y = acc + aux2
+ * Bit-identical to two nn_gemm128 calls.  B1_img / B2_img: nn_gemm128_prepare_b images.  tcgen05 only. */
+#define NN_MID_SILU_SAVE 0
+#define NN_MID_MUL 1
+#define NN_OUT_BIAS 0
+#define NN_OUT_ADD 1
+typedef struct {
+    const float* X; const float* B1_img; const float* B2_img;
+    const float* bias1; const float* bias2;
+    const float* aux1; const float* aux2; float* aux_out;
+    float* Y;
+    const int32_t* m_dev; int32_t m_dev_mul;   /* rows = m_dev[0] * m_dev_mul when m_dev != NULL */
+    int32_t m;
+    int32_t mid, out;
+} nn_gemm_chain_args;
+NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream);
 /* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo
  * parts, laid out as UMMA K-major 128B-swizzled blocks; `image` holds NN_B_IMAGE_FLOATS floats. */
 NN_API int nn_gemm128_prepare_b(const float* B, float* image, void* stream);

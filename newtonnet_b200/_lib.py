@@ -55,6 +55,12 @@ class GemmArgs(C.Structure):
                 ('epilogue', C.c_int32)]
 
 
+class GemmChainArgs(C.Structure):
+    _fields_ = [('X', _fp), ('B1_img', _fp), ('B2_img', _fp), ('bias1', _fp), ('bias2', _fp), ('aux1', _fp), ('aux2', _fp),
+                ('aux_out', _fp), ('Y', _fp), ('m_dev', _fp), ('m_dev_mul', C.c_int32), ('m', C.c_int32), ('mid', C.c_int32),
+                ('out', C.c_int32)]
+
+
 class EvalArgs(C.Structure):
     _fields_ = [('nbr', C.POINTER(Nbr)), ('w', C.POINTER(Weights)), ('z', _fp), ('want_forces', C.c_int32),
                 ('want_virial', C.c_int32), ('n_owned', C.c_int32), ('pad_', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
@@ -92,6 +98,7 @@ SYMBOLS = {
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    'nn_gemm128_chain': (C.c_int, [C.POINTER(GemmChainArgs), _fp]),
     'nn_md_advance': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_double, C.c_double, C.c_uint64, _fp, _fp]),
     'nn_md_finish': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_double, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),

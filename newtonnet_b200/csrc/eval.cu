@@ -44,6 +44,12 @@ extern "C" int nn_version(void) { return 100; }
 #include <vector>
 static std::atomic<long long> g_launches{0};
 void nn_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static bool chain_enabled() {          // two-CTA chained GEMM pairs (gemm_chain.cu); NN_CHAIN=0 falls back to two launches
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NN_CHAIN"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 bool nn_pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("NN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -176,6 +182,36 @@ struct Gemm {
     void bwd(const float* X, const nn_mat& M, float* Y, int m, int pro, int epi, const float* bias = nullptr,
              const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
              const int* m_dev = nullptr) { run(X, M.w, M.w_img, Y, m, pro, epi, bias, aux1, aux2, aux3, m_dev); }
+    // Y = (silu(X @ M1^T + b1)) @ M2^T + b2, silu'(.) left in `mid` (forward MLP); one chained launch when available
+    void mlp_fwd(const float* X, const nn_mat& M1, const float* b1, float* mid, const nn_mat& M2, const float* b2, float* Y,
+                 int m, int pro_act, const int* m_dev = nullptr) {
+        if (rc) return;
+        if (g_backend == 2 && chain_enabled() && m_dev && M1.wt_img && M2.wt_img) {     // pair-level only (gemm_chain.cu)
+            ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
+            nn_gemm_chain_args a{};
+            a.X = X; a.B1_img = M1.wt_img; a.B2_img = M2.wt_img; a.bias1 = b1; a.bias2 = b2; a.aux_out = mid; a.Y = Y;
+            a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_SILU_SAVE; a.out = NN_OUT_BIAS;
+            rc = nn_gemm128_chain(&a, s);
+            return;
+        }
+        fwd(X, M1, mid, m, NN_PRO_NONE, NN_EPI_BIAS, b1, nullptr, nullptr, nullptr, m_dev);
+        fwd(mid, M2, Y, m, pro_act, NN_EPI_BIAS, b2, nullptr, nullptr, nullptr, m_dev);
+    }
+    // Y (+)= ((G @ M2) * dact) @ M1 (reverse MLP); `tmp` receives the intermediate on the two-launch path only
+    void mlp_bwd(const float* G, const nn_mat& M2, const float* dact, float* tmp, const nn_mat& M1, float* Y, int m,
+                 bool accumulate, const int* m_dev = nullptr) {
+        if (rc) return;
+        if (g_backend == 2 && chain_enabled() && m_dev && accumulate && M1.w_img && M2.w_img) {
+            ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
+            nn_gemm_chain_args a{};
+            a.X = G; a.B1_img = M2.w_img; a.B2_img = M1.w_img; a.aux1 = dact; a.aux2 = accumulate ? Y : nullptr; a.Y = Y;
+            a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_MUL; a.out = accumulate ? NN_OUT_ADD : NN_OUT_BIAS;
+            rc = nn_gemm128_chain(&a, s);
+            return;
+        }
+        bwd(G, M2, tmp, m, NN_PRO_NONE, NN_EPI_MUL, nullptr, dact, nullptr, nullptr, m_dev);
+        bwd(tmp, M1, Y, m, NN_PRO_NONE, accumulate ? NN_EPI_ADD : NN_EPI_BIAS, nullptr, accumulate ? Y : nullptr, nullptr, nullptr, m_dev);
+    }
     void run(const float* X, const float* B, const float* B_img, float* Y, int m, int pro, int epi,
              const float* bias = nullptr, const float* aux1 = nullptr, const float* aux2 = nullptr,
              const float* aux3 = nullptr, const int* m_dev = nullptr, int mul = 1) {
@@ -252,8 +288,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
     }
     case NN_PH_FWD_NODE: {   // -> mn(l) of owned atoms            [then ghosts of: mn(l), f_out(l-1)]
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
-        g.fwd(a_cur, lw.W1, b.pre, No, NN_PRO_NONE, NN_EPI_BIAS, lw.b1);
-        g.fwd(b.pre, lw.W2, b.mn, No, c.PRO_ACT, NN_EPI_BIAS, lw.b2);
+        g.mlp_fwd(a_cur, lw.W1, lw.b1, b.pre, lw.W2, lw.b2, b.mn, No, c.PRO_ACT);
         return g.rc;
     }
     case NN_PH_FWD_PAIR: {   // message, edge MLPs, aggregation, equivariant update (R7)
@@ -265,11 +300,9 @@ int run_phase(EvalCtx& c, int phase, int l) {
             if (g_backend >= 1 && lw.We_img) NN_TRY(nn_message_fwd_tc(nl, w.rbf, b.mn, lw.We_img, b.msg, s));
             else NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s));
         }
-        g.fwd(b.msg, lw.U1, b.q1, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-        g.fwd(b.q1, lw.U2, b.e1, P, c.PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.mlp_fwd(b.msg, lw.U1, nullptr, b.q1, lw.U2, nullptr, b.e1, P, c.PRO_ACT, np_dev);
         if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
-            g.fwd(b.msg, lw.V1, b.q2, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
-            g.fwd(b.q2, lw.V2, b.e2, P, c.PRO_ACT, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+            g.mlp_fwd(b.msg, lw.V1, nullptr, b.q2, lw.V2, nullptr, b.e2, P, c.PRO_ACT, np_dev);
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd_rows(nl, No, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
@@ -283,8 +316,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         return 0;
     }
     case NN_PH_HEAD: {       // energy head (R8, R9): partial energies over owned atoms
-        g.fwd(a_cur, W.H1, w.h1pre, No, NN_PRO_NONE, NN_EPI_BIAS, W.hb1);
-        g.fwd(w.h1pre, W.H2, w.h2pre, No, c.PRO_ACT, NN_EPI_BIAS, W.hb2);
+        g.mlp_fwd(a_cur, W.H1, W.hb1, w.h1pre, W.H2, W.hb2, w.h2pre, No, c.PRO_ACT);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd_rows(w.h2pre, W.w3, W.hb3, W.scale, W.shift, c.a->z, nl->sys_ptr, No, c.B, w.e_atom, c.a->energy, s)); }
         if (c.a->direct_force) {   // direct_force head (models/output.py:115-132): no reverse sweep involved
@@ -303,8 +335,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
     }
     case NN_PH_BWD_SEED: {   // reverse sweep (R10 / row B): dE/da of owned atoms
         { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_seed_launch(w.h2pre, W.w3, W.scale, c.a->z, No, w.tmpN, s)); }
-        g.bwd(w.tmpN, W.H2, w.mnbar, No, NN_PRO_NONE, NN_EPI_MUL, nullptr, w.h1pre);
-        g.bwd(w.mnbar, W.H1, w.abar, No, NN_PRO_NONE, NN_EPI_BIAS);
+        g.mlp_bwd(w.tmpN, W.H2, w.h1pre, w.mnbar, W.H1, w.abar, No, false);
         NN_TRY(g.rc);
         cudaMemsetAsync(w.fbar, 0, (size_t)N * 3 * kF * sizeof(float), s);
         cudaMemsetAsync(w.x_bar, 0, (size_t)2 * L * P * sizeof(float), s);
@@ -323,11 +354,9 @@ int run_phase(EvalCtx& c, int phase, int l) {
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
         { ProfScope ps(NN_STAGE_BWD_GATHER, s); NN_TRY(nn_pair_bwd_gather_launch(nl, w.dfb, f_in, w.unit, b.e1, w.e2bar, w.ubar, first, s)); }
         // mbar = ((e1bar @ U2) * silu'(q1)) @ U1 + ((e2bar @ V2) * silu'(q2)) @ V1
-        g.bwd(b.e1, lw.U2, b.e1, P, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.q1, nullptr, nullptr, np_dev);
-        g.bwd(b.e1, lw.U1, w.mbar, P, NN_PRO_NONE, NN_EPI_BIAS, nullptr, nullptr, nullptr, nullptr, np_dev);
+        g.mlp_bwd(b.e1, lw.U2, b.q1, b.e1, lw.U1, w.mbar, P, false, np_dev);
         if (!first) {
-            g.bwd(w.e2bar, lw.V2, w.e2bar, P, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.q2, nullptr, nullptr, np_dev);
-            g.bwd(w.e2bar, lw.V1, w.mbar, P, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.mbar, nullptr, nullptr, np_dev);
+            g.mlp_bwd(w.e2bar, lw.V2, b.q2, w.e2bar, lw.V1, w.mbar, P, true, np_dev);
         }
         NN_TRY(g.rc);
         {
@@ -338,8 +367,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         }
         { ProfScope ps(NN_STAGE_BWD_AGGREGATE, s); NN_TRY(nn_node_aggregate_bwd_launch(nl, No, w.mbar, b.mn, b.e2, w.dfb, w.mnbar, w.fbar, first, s)); }
         // abar += ((mnbar @ W2) * silu'(pre)) @ W1
-        g.bwd(w.mnbar, lw.W2, w.tmpN, No, NN_PRO_NONE, NN_EPI_MUL, nullptr, b.pre);
-        g.bwd(w.tmpN, lw.W1, w.abar, No, NN_PRO_NONE, NN_EPI_ADD, nullptr, w.abar);
+        g.mlp_bwd(w.mnbar, lw.W2, b.pre, w.tmpN, lw.W1, w.abar, No, true);
         return g.rc;
     }
     case NN_PH_FINISH: {     // dE/d disp per pair, forces of owned atoms, partial virial

@@ -1,0 +1,72 @@
+"""Chained two-CTA contraction (csrc/gemm_chain.cu) against two single launches (bit-identical) and fp64."""
+import ctypes as C
+
+import pytest
+import torch
+
+from test_gpu_parity import _gemm, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _chain(lib, X, B1, B2, mid, out, bias1=None, bias2=None, aux1=None, aux2=None, aux_out=None, Y=None, m_dev=None):
+    from newtonnet_b200 import _lib as L
+    s = torch.cuda.current_stream().cuda_stream
+    imgs = []
+    for B in (B1, B2):
+        img = torch.empty(L.NN_B_IMAGE_FLOATS, device=X.device)
+        L.check(lib.nn_gemm128_prepare_b(B.data_ptr(), img.data_ptr(), s), 'prepare_b')
+        imgs.append(img)
+    Y = torch.empty_like(X) if Y is None else Y
+    a = L.GemmChainArgs()
+    a.X, a.B1_img, a.B2_img, a.Y = X.data_ptr(), imgs[0].data_ptr(), imgs[1].data_ptr(), Y.data_ptr()
+    a.bias1, a.bias2, a.aux1, a.aux2, a.aux_out = L.ptr(bias1), L.ptr(bias2), L.ptr(aux1), L.ptr(aux2), L.ptr(aux_out)
+    a.m_dev, a.m_dev_mul, a.m, a.mid, a.out = L.ptr(m_dev), 1, X.shape[0], mid, out
+    L.check(lib.nn_gemm128_chain(C.byref(a), s), 'nn_gemm128_chain')
+    torch.cuda.synchronize()
+    return Y
+
+
+@pytest.mark.parametrize('M', [1, 127, 128, 129, 300, 4099, 74 * 128 * 3 + 77, 148 * 128 * 5 + 1])
+def test_chain_matches_two_launches(M):
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    lib.nn_set_gemm_backend(2)
+    g = torch.Generator(device='cpu').manual_seed(M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev())
+    X, B1, B2, b1, b2, aux, acc0 = r(M, 128), r(128, 128) / 11.3, r(128, 128) / 11.3, r(128), r(128), r(M, 128), r(M, 128)
+    silu = lambda t: t * torch.sigmoid(t)
+    dsilu = lambda t: torch.sigmoid(t) * (1 + t * (1 - torch.sigmoid(t)))
+    # forward MLP: two launches (pre-activation, then SILU_SAVE in place) vs one chained launch
+    pre = _gemm(lib, X, B1, bias=b1)
+    want_mid = pre.clone()
+    want = _gemm(lib, want_mid, B2, pro=L.PRO_SILU_SAVE, bias=b2, aux_out=want_mid)
+    mid = torch.empty_like(X)
+    got = _chain(lib, X, B1, B2, 0, 0, bias1=b1, bias2=b2, aux_out=mid)
+    assert torch.equal(got, want) and torch.equal(mid, want_mid)
+    ref = silu(X.double() @ B1.double() + b1.double()) @ B2.double() + b2.double()
+    torch.testing.assert_close(got.double(), ref, rtol=3e-5, atol=3e-5)
+    torch.testing.assert_close(mid.double(), dsilu(X.double() @ B1.double() + b1.double()), rtol=2e-5, atol=2e-6)
+    # no biases
+    assert torch.equal(_chain(lib, X, B1, B2, 0, 0, aux_out=mid),
+                       _gemm(lib, _gemm(lib, X, B1), B2, pro=L.PRO_SILU))
+    # reverse MLP: (X @ B1) * aux @ B2 [+ acc]
+    t = _gemm(lib, X, B1, epi=L.EPI_MUL, aux1=aux)
+    assert torch.equal(_chain(lib, X, B1, B2, 1, 0, aux1=aux), _gemm(lib, t, B2))
+    want_acc = acc0.clone(); _gemm(lib, t, B2, epi=L.EPI_ADD, aux1=want_acc, Y=want_acc)
+    got_acc = acc0.clone(); _chain(lib, X, B1, B2, 1, 1, aux1=aux, aux2=got_acc, Y=got_acc)
+    assert torch.equal(got_acc, want_acc)
+    # device-side row count below the launch capacity: rows beyond it are untouched
+    if M > 130:
+        cnt = torch.tensor([M - 100], dtype=torch.int32, device=dev())
+        Y = torch.full_like(X, 7.0); mid = torch.full_like(X, 5.0)
+        _chain(lib, X, B1, B2, 0, 0, bias1=b1, bias2=b2, aux_out=mid, Y=Y, m_dev=cnt)
+        assert torch.equal(Y[:M - 100], want[:M - 100]) and bool((Y[M - 100:] == 7.0).all()) and bool((mid[M - 100:] == 5.0).all())
+
+
+def test_chain_argument_errors():
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    a = L.GemmChainArgs()
+    assert lib.nn_gemm128_chain(C.byref(a), None) != 0
+    assert b'null' in lib.nn_last_error()
