@@ -368,6 +368,7 @@ def main_b200(args):
     stage_n = {L.STAGES[k]: int(cnt[k]) for k in range(12)}
     n_layers = pack.n_layers
     F = 128
+    chained = backend == 'ts' and os.environ.get('NN_CHAIN', '1') != '0'
     # algorithmic work per launch (DESIGN.md section "kernels"): GEMM = 2*M*128*128 flop and 2*M*512 B
     alg = {
         # 32 flop per byte algorithmic (2*128*128 flop per 1 KB row) << machine balance: the GEMMs are HBM-bound
@@ -381,8 +382,10 @@ def main_b200(args):
     }
     # stages whose launches differ (first layer skips the e2 / f_j streams): use the per-step total instead
     per_step_total = {
-        # per pair: layer 0 (U path only) fwd 1024 + 1536, bwd 1536 + 1024; other layers fwd 2*(1024 + 1536), bwd 2*1536 + 1024 + 1536
-        'pair_gemm': P * (5120.0 + (n_layers - 1) * 10752.0),
+        # per pair, two launches per MLP: layer 0 (U path only) fwd 1024 + 1536, bwd 1536 + 1024; other layers fwd 2*(1024 + 1536),
+        # bwd 2*1536 + 1024 + 1536.  With the chained two-CTA kernel (gemm_chain.cu: forward MLPs and the accumulating reverse
+        # MLP) the intermediate never reaches HBM: forward MLP 1536, accumulating reverse MLP 2048.
+        'pair_gemm': P * ((4096.0 + (n_layers - 1) * 7680.0) if chained else (5120.0 + (n_layers - 1) * 10752.0)),
         'node_gemm': 2.0 * F * F * N * (n_layers * (2 + 3 + 3 + 2) + 4),
         'aggregate': (n_layers * (P * 2 * 512 + N * (512 * 2 + 1536) + 2 * P * 8 + P * 12) + (n_layers - 1) * (P * 512 + N * 1536 * 2)),
         'bwd_gather': (n_layers * (P * (1024 + 8 + 24) + N * 1536) + (n_layers - 1) * (P * 512 + N * 1536)),
@@ -409,9 +412,13 @@ def main_b200(args):
         if dominant == 'pair_gemm':   # the same launches as fp32-equivalent FLOP/s (one 2*128*128 product per row)
             roofline['tflops_fp32_equivalent'] = 2.0 * P * F * F * t['launches'] / K / (t['ms_total'] * 1e-3 / K) * 1e-12
             roofline['tensor_pipe_passes'] = 3
-        if dominant == 'pair_gemm' and args.workload == 'c2':
-            # ncu --set full on this workload (profiles/ncu_r1/k_gemm128_ts.raw.csv): the multiply-epilogue variant
-            # moves dram read 1.847 GB + write 0.887 GB per launch for 1536 B x 1,802,624 rows = 2.769 GB algorithmic
+        if dominant == 'pair_gemm' and args.workload == 'c2' and chained:
+            # ncu dram__bytes_read + dram__bytes_write of every pair-level GEMM launch of one step (profiles/r1c_gemm_dram.csv):
+            # 5 x chain<fwd> 2.706 GB + 3 x (MUL 2.731 + plain 1.788) + 2 x chain<bwd,add> 3.655 = 34.40 GB in 13 launches;
+            # algorithmic 19,456 B x 1,802,624 pairs = 35.07 GB
+            roofline['traffic'] = 34.40e9 / 13
+            roofline['traffic_note'] = 'average DRAM bytes per pair-level GEMM launch (ncu, 13 launches per step); algorithmic 35.07e9 / 13'
+        elif dominant == 'pair_gemm' and args.workload == 'c2':
             roofline['traffic'] = 2.734e9
             roofline['traffic_note'] = 'bytes per launch of the <NONE,MUL> variant (ncu dram__bytes_read+write); algorithmic 2.769e9'
 
@@ -426,7 +433,7 @@ def main_b200(args):
         'config': {'workload': f'{args.workload}: {workloads.DESCRIPTION[args.workload]}', 'atoms_per_gpu': N,
                    'systems_per_gpu': B, 'directed_edges_per_gpu': n_edges, 'n_features': 128, 'n_basis': 20,
                    'n_interactions': n_layers, 'cutoff': pack.cutoff, 'heads': props,
-                   'gemm_backend': {'simt': 'fp32 SIMT', 'tc': 'tcgen05 3xTF32 (A, B in smem)', 'ts': 'tcgen05 3xTF32 (A in TMEM)'}[backend],
+                   'gemm_backend': {'simt': 'fp32 SIMT', 'tc': 'tcgen05 3xTF32 (A, B in smem)', 'ts': 'tcgen05 3xTF32 (A in TMEM)'}[backend] + (', chained two-CTA MLPs' if chained else ''),
                    'parallelism': f'dp{world} (independent batches, no data-path collective)',
                    'cache': 'per-step working set (pair tensors, %.1f GB) exceeds the 126 MB L2; positions change every step'
                             % (n_layers * 5 * P * 512 / 1e9)},
