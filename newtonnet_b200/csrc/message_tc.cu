@@ -28,6 +28,14 @@ constexpr uint32_t BAR_BYTES = 256;
 // (epilogue) = 2048 = 16 x 128
 constexpr int REGS_PROD = 104, REGS_MMA = 40, REGS_EPI = 184;
 
+// gather window of the epilogue (tools/build_variant.sh overrides these for A/B runs)
+#ifndef NN_MSG_FWD_G
+#define NN_MSG_FWD_G 4
+#define NN_MSG_FWD_D 2
+#define NN_MSG_BWD_G 2
+#define NN_MSG_BWD_D 2
+#endif
+
 template <bool BWD> struct Cfg {
     static constexpr int NA = BWD ? 2 : 1;              // A operands per tile (rbf [, drbf])
     static constexpr uint32_t A_STAGE_BYTES = NA * 2 * BLK_BYTES;
@@ -35,12 +43,6 @@ template <bool BWD> struct Cfg {
     static constexpr uint32_t TMEM_COLS = BWD ? 512 : 256;
     static constexpr uint32_t ACC_COLS = BWD ? 256 : 128;   // columns per accumulator buffer
     static constexpr int PF = BWD ? 1 : 2;              // tiles of rbf rows in flight in registers per producer thread
-#ifndef NN_MSG_FWD_G
-#define NN_MSG_FWD_G 4
-#define NN_MSG_FWD_D 2
-#define NN_MSG_BWD_G 2
-#define NN_MSG_BWD_D 2
-#endif
     static constexpr int G = BWD ? NN_MSG_BWD_G : NN_MSG_FWD_G;   // rows per lane in one gather group
     static constexpr int D = BWD ? NN_MSG_BWD_D : NN_MSG_FWD_D;   // window depth: D - 1 groups in flight behind the one being consumed
 };
