@@ -57,6 +57,29 @@ def read_extxyz(path, limit=None, length_unit=1.0, energy_unit=1.0):
     return frames
 
 
+def write_extxyz(path, frames, append=False):
+    """Frames ({z, pos[, cell, energy, force]}) -> extended xyz in the layout read_extxyz / the reference's data files use."""
+    with open(path, 'a' if append else 'w') as fh:
+        for f in frames:
+            z, pos = np.asarray(f['z']), np.asarray(f['pos'], dtype=np.float64)
+            force = f.get('force')
+            cell = f.get('cell')
+            periodic = cell is not None and np.any(np.asarray(cell) != 0)
+            head = 'Properties=species:S:1:pos:R:3' + (':forces:R:3' if force is not None else '')
+            if f.get('energy') is not None:
+                head += ' energy=%.10f' % float(f['energy'])
+            if periodic:
+                head = 'Lattice="%s" ' % ' '.join('%.10f' % x for x in np.asarray(cell, dtype=np.float64).reshape(-1)) + head + ' pbc="T T T"'
+            else:
+                head += ' pbc="F F F"'
+            fh.write('%d\n%s\n' % (len(z), head))
+            for k in range(len(z)):
+                row = '%s %.10f %.10f %.10f' % (SYMBOLS[int(z[k])], *pos[k])
+                if force is not None:
+                    row += ' %.10f %.10f %.10f' % tuple(np.asarray(force, dtype=np.float64)[k])
+                fh.write(row + '\n')
+
+
 def collate(frames, device=None, dtype=torch.float32):
     """Concatenate frames into the (z, pos, cell, batch, energy, force) tensors NewtonNet.forward / training_step take."""
     z = torch.from_numpy(np.concatenate([f['z'] for f in frames]))

@@ -166,12 +166,17 @@ class DeviceMD:
         self.kernels_per_step = int(self.lib.nn_launch_count(0) - before)     # kernels one graph replay launches
 
     # ------------------------------------------------------------------ run
-    def run(self, steps):
-        """Advance `steps` time steps.  Returns {'energy': [steps, B], 'kinetic': [steps, B]} (numpy fp64, eV)."""
-        pe, ke = [], []
+    def run(self, steps, trajectory_interval=None):
+        """Advance `steps` time steps.  Returns {'energy': [steps, B], 'kinetic': [steps, B]} (numpy fp64, eV) and, with
+        trajectory_interval = k, 'positions': [steps // k, N, 3] (unwrapped, fp64) sampled after every k-th step - the
+        device-side counterpart of the `trajectory=..., loginterval=k` arguments of the reference's ASE driver
+        (scripts/simulate.py:21-30); the copy happens at chunk boundaries, so chunks are cut at multiples of k."""
+        pe, ke, traj = [], [], []
         done = 0
         while done < steps:
             n = min(self.check_interval, steps - done)
+            if trajectory_interval:
+                n = min(n, trajectory_interval - (done % trajectory_interval))
             snap = (self.x.clone(), self.v.clone(), self.force.clone(), self.step_ctr.clone())
             s0 = int(snap[3].item())
             for _ in range(n):
@@ -192,8 +197,13 @@ class DeviceMD:
             chunk = self.log[rows].cpu().numpy()
             pe.append(chunk[:, :, 0]); ke.append(chunk[:, :, 1])
             done += n
+            if trajectory_interval and done % trajectory_interval == 0:
+                traj.append(self.x.cpu().numpy())
         empty = np.zeros((0, self.n_systems))
-        return {'energy': np.concatenate(pe) if pe else empty, 'kinetic': np.concatenate(ke) if ke else empty}
+        out = {'energy': np.concatenate(pe) if pe else empty, 'kinetic': np.concatenate(ke) if ke else empty}
+        if trajectory_interval:
+            out['positions'] = np.stack(traj) if traj else np.zeros((0, self.n_atoms, 3))
+        return out
 
     # ------------------------------------------------------------------ state
     @property

@@ -92,3 +92,19 @@ def test_fit_scalers_sets_energy_scale_shift():
     np.testing.assert_allclose(model.scalers[0].shift.weight.detach().numpy()[:, 0], g['e_shift'].astype(np.float32), rtol=1e-6)
     np.testing.assert_allclose(model.scalers[0].scale.weight.detach().numpy()[:, 0], g['e_scale'].astype(np.float32), rtol=1e-6)
     assert model.scalers[0].shift.weight.dtype == torch.float32
+
+
+def test_write_extxyz_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    cell = np.diag([9.0, 10.0, 11.0])
+    frames = [{'z': np.array([8, 1, 1]), 'pos': rng.uniform(0, 9, (3, 3)), 'cell': cell, 'energy': -1.5, 'force': rng.normal(size=(3, 3))},
+              {'z': np.array([6, 1]), 'pos': rng.uniform(0, 9, (2, 3)), 'cell': cell, 'energy': 2.25, 'force': rng.normal(size=(2, 3))}]
+    D.write_extxyz(str(tmp_path / 'w.xyz'), frames)
+    D.write_extxyz(str(tmp_path / 'w.xyz'), [{'z': np.array([1]), 'pos': np.zeros((1, 3))}], append=True)
+    got = D.read_extxyz(str(tmp_path / 'w.xyz'))
+    assert len(got) == 3 and got[2]['energy'] is None and got[2]['force'] is None and (got[2]['cell'] == 0).all()
+    for f, g in zip(frames, got):
+        assert (f['z'] == g['z']).all() and abs(f['energy'] - g['energy']) < 1e-9
+        np.testing.assert_allclose(g['pos'], f['pos'], atol=1e-8)
+        np.testing.assert_allclose(g['force'], f['force'], atol=1e-8)
+        np.testing.assert_allclose(g['cell'], cell, atol=1e-8)

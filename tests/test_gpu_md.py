@@ -84,6 +84,9 @@ def test_nve_matches_host_velocity_verlet():
     ke = np.array([0.5 * (ATOMIC_MASSES[z] * (v ** 2).sum(-1))[batch == b].sum() for b in range(3)])
     np.testing.assert_allclose(out['kinetic'][-1], ke, rtol=1e-5)
     assert md.step == steps and md.graph_launches == steps
+    more = md.run(12, trajectory_interval=5)          # snapshots after steps 5 and 10 of this call
+    assert more['positions'].shape == (2, len(z), 3) and more['energy'].shape == (12, 3)
+    assert np.abs(more['positions'][1] - md.positions).max() > 0 and md.step == steps + 12
 
 
 def test_nve_energy_conservation():
