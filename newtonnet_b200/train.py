@@ -30,14 +30,36 @@ def _stream():
 
 
 # ----------------------------------------------------------------------------- raw kernel calls
-def _gemm_raw(X, B):
+# Operand images of the model's weights, valid for ONE training step: every nn.Linear weight is multiplied in both
+# orientations several times per step (forward, backward, double backward).  Only views of leaf parameters are cached
+# (temporaries can reuse an address), keyed by storage address, version and strides; differentiable_forward clears the
+# cache when a step begins, so a CUDA-graph capture always records the prepare kernels of its own step.
+_image_cache = {}
+
+
+def _operand_image(B, Bc):
+    lib = L.load()
+    base = B._base if B._base is not None else B
+    key = None
+    if base.is_leaf and isinstance(base, torch.nn.Parameter):
+        key = (B.data_ptr(), base._version, tuple(B.shape), tuple(B.stride()))
+        img = _image_cache.get(key)
+        if img is not None:
+            return img
+    img = torch.empty(L.NN_B_IMAGE_FLOATS, dtype=torch.float32, device=Bc.device)
+    L.check(lib.nn_gemm128_prepare_b(Bc.data_ptr(), img.data_ptr(), _stream()), 'nn_gemm128_prepare_b')
+    if key is not None:
+        _image_cache[key] = img
+    return img
+
+
+def _gemm_raw(X, B, B_orig=None):
     lib = L.load()
     M = X.shape[0]
     Y = torch.empty(M, 128, dtype=torch.float32, device=X.device)
     if M == 0:
         return Y
-    img = torch.empty(L.NN_B_IMAGE_FLOATS, dtype=torch.float32, device=X.device)
-    L.check(lib.nn_gemm128_prepare_b(B.data_ptr(), img.data_ptr(), _stream()), 'nn_gemm128_prepare_b')
+    img = _operand_image(B if B_orig is None else B_orig, B)
     a = L.GemmArgs()
     a.X, a.B, a.B_img, a.Y, a.m = X.data_ptr(), B.data_ptr(), img.data_ptr(), Y.data_ptr(), M
     L.check(lib.nn_gemm128(C.byref(a), _stream()), 'nn_gemm128')
@@ -65,7 +87,7 @@ class Gemm(torch.autograd.Function):
         # save the inputs themselves: a contiguous copy made here would be cut off from the graph, and
         # the double backward needs d(dX)/dB through them
         ctx.save_for_backward(X, B)
-        return _gemm_raw(_c(X), _c(B))
+        return _gemm_raw(_c(X), _c(B), B)
 
     @staticmethod
     def backward(ctx, dY):
@@ -214,6 +236,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     dev = pos.device
     cutoff = model.cutoff
     N, F = pos.shape[0], L.NN_F
+    _image_cache.clear()                                    # operand images live for one step
     if model.embedding_layers.requires_dr and pos.is_leaf and not pos.requires_grad:
         pos.requires_grad = True
     # ---- edges (reference order) from the cell-list kernel; image shifts are constants of the graph
