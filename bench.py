@@ -528,7 +528,7 @@ def main_c5_training(args, world, rank, local, dev, lib, backend, barrier, max_o
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     args_t = (t(z), t(pos), t(cell), t(batch), e_t, f_t)
     # NN_TRAIN_GRAPH=1: forward + double backward replayed as one CUDA graph (static, padded edge list).  Measured on c5:
-    # 23.2 ms vs 22.0 ms eager - the step is bound by ~1,500 small kernels on the GPU, not by the host - so eager is the default
+    # 18.2 ms vs 18.5 ms eager - the step is bound by ~1,400 small kernels on the GPU, not by the host - so eager is the default
     graphed = os.environ.get('NN_TRAIN_GRAPH', '0') == '1'
     if graphed:
         from newtonnet_b200.train import GraphedTrainingStep

@@ -358,7 +358,7 @@ class GraphedTrainingStep:
     """training_step with forward + double backward replayed as ONE CUDA graph (static batch shape).
 
     Removes every host synchronisation and all Python / autograd dispatch from the step.  Measured on config 5 (100 x 21
-    atoms, B200): 23.2 ms against 22.0 ms eager - the step is bound by ~1,500 small kernels on the GPU, not by the host,
+    atoms, B200): 18.2 ms against 18.5 ms eager - the step is bound by ~1,400 small kernels on the GPU, not by the host,
     so this is an option (busy hosts, many ranks per host), not the default.  Shapes are made static by
     padding the edge list to the neighbour list's capacity (see `_edges`); the neighbour rebuild, the forward, the loss
     and loss.backward() are captured once, every later call copies the batch into the static buffers and replays.
