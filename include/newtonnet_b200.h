@@ -311,6 +311,30 @@ NN_API int nn_segment_sum(const float* src, const int32_t* perm, const int32_t* 
 NN_API size_t nn_gemm128_tn_workspace_bytes(int32_t m);
 NN_API int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream);
 
+/* ---- reverse-sweep operators as standalone entry points; nn_eval composes exactly these.
+ * They replace the autograd replay of DerivativeProperty._save_grad (models/output.py:66-73) piece by piece. */
+/* Y = silu(X M1^T + b1) M2^T + b2; `mid` receives the pre-activation, or silu'(pre-activation) when save_dact != 0 (what
+ * nn_mlp_bwd consumes).  m_dev != NULL: pair-level call, rows = m_dev[0] <= m.  One chained launch where it pays. */
+NN_API int nn_mlp_fwd(const float* X, const nn_mat* M1, const float* b1, float* mid, const nn_mat* M2, const float* b2, float* Y,
+                      int32_t m, const int32_t* m_dev, int32_t save_dact, void* stream);
+/* Y (+)= ((G M2) * dact) M1: the transpose of nn_mlp_fwd with respect to X.  `tmp` [m,128] may alias G. */
+NN_API int nn_mlp_bwd(const float* G, const nn_mat* M2, const float* dact, float* tmp, const nn_mat* M1, float* Y, int32_t m,
+                      const int32_t* m_dev, int32_t accumulate, void* stream);
+/* gh2[i,:] = scale[z_i] * w3 * silu'(h2pre[i,:]): d(sum of atomic energies)/d(second hidden layer), models/output.py:98-100 */
+NN_API int nn_energy_head_bwd(const float* h2pre, const float* w3, const float* scale, const int64_t* z, int32_t n_atoms,
+                              float* gh2, void* stream);
+/* per pair p = (i<j), with w[c] = dfb_i[c] - dfb_j[c]:  ubar_p[c] += <w[c], e1_p>;  e1_io_p <- sum_c w[c] u_p[c]  (in place);
+ * e2bar_p = sum_c dfb_i[c] * f_in_j[c] + dfb_j[c] * f_in_i[c]  (skipped when f_in == NULL: first layer).  dfb, f_in [N,3,128]. */
+NN_API int nn_pair_gather_bwd(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
+                              float* e2bar, float* ubar, void* stream);
+/* mt = mbar_p + abar_i + abar_j;  y = mt * mn_i * mn_j;  x_part <- <y, We drbf_p> (tensor-core backend: two partial sums
+ * x_part[0][p] + x_part[1][p] over the column halves; SIMT: x_part[0][p], row 1 untouched);  mbar_io_p <- mt * (We rbf_p). */
+NN_API int nn_edge_message_bwd(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
+                               const float* Wet, const float* We_img, float* mbar_io, float* x_part, void* stream);
+/* mnbar_k = sum_{e=(k,i)} t_p(e) * mn_i;  fbar_new_k[c] = dfb_k[c] + sum_{e=(k,i)} dfb_i[c] * e2_p(e)  (skipped when e2 == NULL) */
+NN_API int nn_node_aggregate_bwd(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
+                                 float* mnbar, float* fbar_new, void* stream);
+
 /* ---- device-resident molecular dynamics (caller side of the path) --------------------
  * Replaces the per-step host loop of the reference's MD driver: scripts/simulate.py:21-31 (ASE Langevin) calling
  * MLAseCalculator.calculate, utils/ase_interface.py:52-81, i.e. numpy -> H2D -> forward -> D2H every step.

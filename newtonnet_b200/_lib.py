@@ -99,6 +99,12 @@ SYMBOLS = {
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
     'nn_gemm128_chain': (C.c_int, [C.POINTER(GemmChainArgs), _fp]),
+    'nn_mlp_fwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, _fp, C.c_int32, _fp, C.c_int32, _fp]),
+    'nn_mlp_bwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, C.c_int32, _fp, C.c_int32, _fp]),
+    'nn_energy_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),
+    'nn_pair_gather_bwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    'nn_edge_message_bwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    'nn_node_aggregate_bwd': (C.c_int, [C.POINTER(Nbr), _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     'nn_md_advance': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_double, C.c_double, C.c_uint64, _fp, _fp]),
     'nn_md_finish': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_double, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     'nn_edge_geom_fwd': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),

@@ -384,6 +384,55 @@ int run_phase(EvalCtx& c, int phase, int l) {
 
 }  // namespace
 
+// ---------------------------------------------------------------- reverse-sweep operators as standalone entry points
+// (SURVEY.md section 8b lists forward / backward pairs; nn_eval composes exactly these launchers)
+extern "C" NN_API int nn_mlp_fwd(const float* X, const nn_mat* M1, const float* b1, float* mid, const nn_mat* M2, const float* b2,
+                                 float* Y, int32_t m, const int32_t* m_dev, int32_t save_dact, void* stream) {
+    NN_REQUIRE(X && M1 && M2 && mid && Y, "null pointer");
+    Gemm g{(cudaStream_t)stream};
+    g.mlp_fwd(X, *M1, b1, mid, *M2, b2, Y, m, save_dact ? NN_PRO_SILU_SAVE : NN_PRO_SILU, m_dev);
+    if (g.rc) return g.rc;
+    NN_CHECK_LAUNCH("nn_mlp_fwd");
+    return 0;
+}
+
+extern "C" NN_API int nn_mlp_bwd(const float* G, const nn_mat* M2, const float* dact, float* tmp, const nn_mat* M1, float* Y,
+                                 int32_t m, const int32_t* m_dev, int32_t accumulate, void* stream) {
+    NN_REQUIRE(G && M1 && M2 && dact && tmp && Y, "null pointer");
+    Gemm g{(cudaStream_t)stream};
+    g.mlp_bwd(G, *M2, dact, tmp, *M1, Y, m, accumulate != 0, m_dev);
+    if (g.rc) return g.rc;
+    NN_CHECK_LAUNCH("nn_mlp_bwd");
+    return 0;
+}
+
+extern "C" NN_API int nn_energy_head_bwd(const float* h2pre, const float* w3, const float* scale, const int64_t* z, int32_t n_atoms,
+                                         float* gh2, void* stream) {
+    NN_REQUIRE(h2pre && w3 && scale && z && gh2, "null pointer");
+    return nn_energy_head_seed_launch(h2pre, w3, scale, z, n_atoms, gh2, (cudaStream_t)stream);
+}
+
+extern "C" NN_API int nn_pair_gather_bwd(const nn_nbr* nl, const float* dfb, const float* f_in, const float* unit, float* e1_io,
+                                         float* e2bar, float* ubar, void* stream) {
+    NN_REQUIRE(nl && dfb && unit && e1_io && ubar && (f_in == nullptr || e2bar != nullptr), "null pointer");
+    return nn_pair_bwd_gather_launch(nl, dfb, f_in, unit, e1_io, e2bar, ubar, f_in == nullptr, (cudaStream_t)stream);
+}
+
+extern "C" NN_API int nn_edge_message_bwd(const nn_nbr* nl, const float* abar, const float* mn, const float* rbf, const float* drbf,
+                                          const float* Wet, const float* We_img, float* mbar_io, float* x_part, void* stream) {
+    NN_REQUIRE(nl && abar && mn && rbf && drbf && mbar_io && x_part && (Wet || We_img), "null pointer");
+    if (g_backend >= 1 && We_img) return nn_message_bwd_tc(nl, abar, mn, rbf, drbf, We_img, mbar_io, x_part, (cudaStream_t)stream);
+    NN_REQUIRE(Wet != nullptr, "the SIMT backend needs Wet");
+    return nn_pair_bwd_message_launch(nl, abar, mn, rbf, drbf, Wet, mbar_io, x_part, (cudaStream_t)stream);
+}
+
+extern "C" NN_API int nn_node_aggregate_bwd(const nn_nbr* nl, const float* t, const float* mn, const float* e2, const float* dfb,
+                                            float* mnbar, float* fbar_new, void* stream) {
+    NN_REQUIRE(nl && t && mn && mnbar && (e2 == nullptr || (dfb && fbar_new)), "null pointer");
+    const int rows = nl->n_owned > 0 ? nl->n_owned : nl->n_atoms;
+    return nn_node_aggregate_bwd_launch(nl, rows, t, mn, e2, dfb, mnbar, fbar_new, e2 == nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int nn_eval_phase(const nn_eval_args* a, int32_t phase, int32_t layer, void* stream) {
     EvalCtx c;
     NN_TRY(make_ctx(a, stream, c));
