@@ -42,3 +42,17 @@ def test_wrap():
     s = (w - p) @ np.linalg.inv(cell)
     assert np.allclose(s, np.rint(s))
     assert (M.wrap(p, np.zeros((3, 3))) == p).all()
+
+
+def test_md_units_and_masses():
+    from newtonnet_b200 import md
+    # ASE units (CODATA 2014): 1 fs = 1e-5 sqrt(e / amu) Angstrom sqrt(amu / eV); kB in eV / K
+    assert abs(md.FS - 0.09822694788464063) < 1e-15 and abs(md.KB - 8.6173303e-5) < 1e-12
+    assert abs(md.ATOMIC_MASSES[1] - 1.008) < 1e-9 and abs(md.ATOMIC_MASSES[6] - 12.011) < 1e-9 and abs(md.ATOMIC_MASSES[8] - 15.999) < 1e-9
+    assert len(md.ATOMIC_MASSES) == 37 and md.ATOMIC_MASSES[0] == 0.0      # H..Kr; heavier elements need explicit masses
+    # equipartition: velocities drawn as sqrt(kT / m) N(0,1) give <m v^2> = kT per degree of freedom
+    rng = np.random.default_rng(0)
+    m = np.array([1.008, 12.011, 15.999] * 4000)
+    v = rng.normal(size=(len(m), 3)) * np.sqrt(md.KB * 300.0 / m)[:, None]
+    t = (m[:, None] * v ** 2).sum() / (3 * len(m) * md.KB)
+    assert abs(t - 300.0) < 5.0
