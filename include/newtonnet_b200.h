@@ -240,7 +240,15 @@ NN_API int nn_eval(const nn_eval_args* a, void* stream);
  *   BWD_SEED, then per layer l = L-1..0: BWD_NODE(l) [dfb, abar], BWD_PAIR(l); FINISH.
  * energy / virial / stress then hold this rank's partial sums, forces the owned rows. */
 enum { NN_PH_BEGIN = 0, NN_PH_FWD_NODE = 1, NN_PH_FWD_PAIR = 2, NN_PH_HEAD = 3, NN_PH_BWD_SEED = 4,
-       NN_PH_BWD_NODE = 5, NN_PH_BWD_PAIR = 6, NN_PH_FINISH = 7 };
+       NN_PH_BWD_NODE = 5, NN_PH_BWD_PAIR = 6, NN_PH_FINISH = 7,
+       /* finer split, so that exchanges off the critical path can run on a second stream:
+        * FWD_PAIR = FWD_PAIR_A (message, edge MLPs, aggregation: needs ghost mn(l), f_out(l-1); produces f_out(l)) +
+        *            FWD_PAIR_B (equivariant update, layer norm: owned rows only);
+        * BWD_NODE = BWD_NORM (layer-norm reverse: abar(l) final) + BWD_NODE_B (dfb);
+        * BWD_PAIR = BWD_PAIR_A (pair gather + reverse edge MLPs: needs ghost dfb, f_out(l-1)) +
+        *            BWD_PAIR_B (reverse message, aggregation, node MLP: needs ghost abar, mn(l)) */
+       NN_PH_FWD_PAIR_A = 8, NN_PH_FWD_PAIR_B = 9, NN_PH_BWD_NORM = 10, NN_PH_BWD_NODE_B = 11,
+       NN_PH_BWD_PAIR_A = 12, NN_PH_BWD_PAIR_B = 13 };
 enum { NN_BUF_MN = 0, NN_BUF_F_OUT = 1, NN_BUF_DFB = 2, NN_BUF_ABAR = 3 };
 NN_API int nn_eval_phase(const nn_eval_args* a, int32_t phase, int32_t layer, void* stream);
 /* device pointer of an exchanged buffer inside the workspace: MN [N,F], F_OUT [N,3,F] (per layer),
@@ -282,23 +290,71 @@ NN_API int nn_energy_head_fwd(const float* h2pre, const float* w3, const float* 
 NN_API int nn_force_virial_reduce(const nn_nbr* nl, const float* disp_bar, float* forces, float* virial,
                            float* stress, void* workspace, void* stream);
 
-/* ------------------------------------------------------------------ halo exchange over NVLink peer memory
- * The pack kernel stores the rows a rank owes its peers directly into the peers' landing buffers (P2P
- * stores through NVSwitch) and then raises flag[my_rank] = epoch in each peer's flag array; nn_halo_wait
- * spins (bounded) on the local flags.  Buffers come from nn_p2p_alloc (plain cudaMalloc, zero-filled) so
- * that CUDA IPC handles (64 bytes, exchanged by the caller) can map them into the other processes. */
+/* ------------------------------------------------------------------ domain decomposition over NVLink peer memory
+ * SURVEY.md section 8e (the reference itself is single-process: layers/representations.py:72-93 is one dense mesh).
+ * Every rank owns one arena from nn_p2p_alloc (plain cudaMalloc, zero-filled, so that CUDA IPC handles - 64 bytes,
+ * exchanged by the caller - can map it into the other processes): landing buffers for ghost feature rows, flag words,
+ * the complete force array [n_atoms_total,3] and a table of per-rank partial sums.  The step counter the flag epochs
+ * derive from lives in device memory, so one decomposed evaluation (nn_dd_begin, nn_nbr_*, nn_eval_phase interleaved
+ * with nn_dd_halo_push / nn_dd_halo_wait, nn_dd_finish) is capturable as ONE CUDA graph; there is no NCCL call on the
+ * data path.  Channels: independent (landing buffers, flags, epoch sequence) triples so that a second stream can
+ * exchange rows off the critical path; every rank must issue the same sequence seq = 0 .. stride[channel]-1 of
+ * exchanges per channel and step (nn_dd_finish is the last exchange of channel 0). */
+#define NN_DD_MAX_RANKS 16
+#define NN_DD_CHANNELS 2
+#define NN_DD_MAX_WIDTH 384         /* floats per exchanged row: F or 3F */
+#define NN_DD_PARTIAL 32            /* floats per rank in the partial table */
+#define NN_DD_STATUS_WORDS 8
+enum { NN_DD_ST_STALE = 0,          /* an owned atom moved more than skin/2 since the plan was made: replan */
+       NN_DD_ST_TIMEOUT = 1,        /* a peer did not publish its flag within ~2 s */
+       NN_DD_ST_OVERFLOW = 2,       /* some rank's neighbour list outgrew its capacity */
+       NN_DD_ST_BAD_INPUT = 3,      /* row overflow / unsorted batch / singular cell on some rank */
+       NN_DD_ST_STEP = 4,           /* device step counter */
+       NN_DD_ST_EDGES = 5 };        /* directed edges summed over ranks / 1024 */
+typedef struct {
+    int32_t world, rank, n_atoms_total, n_owned, n_ghost, pad_;
+    int32_t stride[NN_DD_CHANNELS];                     /* exchanges per step on each channel */
+    /* this rank's arena */
+    float* landing[NN_DD_CHANNELS][2];                  /* [n_ghost, NN_DD_MAX_WIDTH] each, alternating by epoch parity */
+    int32_t* flags[NN_DD_CHANNELS];                     /* [world]: last epoch each source rank has published here */
+    float* forces_full;                                 /* [n_atoms_total, 3] */
+    float* partials;                                    /* [world, NN_DD_PARTIAL] */
+    /* the same regions of the other ranks, mapped into this process (index = rank; own entries unused) */
+    float* peer_landing[NN_DD_CHANNELS][2][NN_DD_MAX_RANKS];
+    int32_t* peer_flags[NN_DD_CHANNELS][NN_DD_MAX_RANKS];
+    float* peer_forces_full[NN_DD_MAX_RANKS];
+    float* peer_partials[NN_DD_MAX_RANKS];
+    /* send plan: local rows send_idx[send_begin[s] .. send_end[s]) go to rank s and land at row row_offset[s] of its
+     * ghost order; ranges are contiguous in rank order (own range empty) */
+    const int32_t* send_idx;
+    int32_t send_begin[NN_DD_MAX_RANKS], send_end[NN_DD_MAX_RANKS], row_offset[NN_DD_MAX_RANKS];
+    int32_t* step;                                      /* device, 1 int: step counter */
+    uint32_t* done;                                     /* device, NN_DD_CHANNELS zeroed counters */
+    int32_t* status;                                    /* device, NN_DD_STATUS_WORDS (local flags) */
+} nn_dd_comm;
 NN_API int nn_p2p_alloc(size_t bytes, void** ptr);
 NN_API int nn_p2p_free(void* ptr);
 NN_API int nn_p2p_get_handle(void* ptr, void* handle64);
 NN_API int nn_p2p_open_handle(const void* handle64, void** ptr);
 NN_API int nn_p2p_close_handle(void* ptr);
-NN_API int nn_halo_push(const float* src, const int32_t* send_idx, int32_t width, int32_t n_peers,
-                        float* const* landing, int32_t* const* flags, const int32_t* row_offset,
-                        const int32_t* send_begin, const int32_t* send_end, int32_t my_rank, int32_t epoch,
-                        uint32_t* done_counter, void* stream);
-NN_API int nn_copy_d2d(void* dst, const void* src, size_t bytes, void* stream);
-NN_API int nn_halo_wait(int32_t* flags, const int32_t* expect, int32_t world, int32_t epoch, int32_t* status,
-                        void* stream);
+/* starts a step: pos_local[i] = pos[l2g[i]], z_local[i] = z[l2g[i]] for the n_local = n_owned + n_ghost local atoms;
+ * raises the sticky STALE flag when an owned atom is further than skin/2 from pos_ref or the cell differs from
+ * cell_ref (the state the brick / ghost plan was made for); advances the step counter. */
+NN_API int nn_dd_begin(const nn_dd_comm* c, const float* pos, const float* pos_ref, const float* cell, const float* cell_ref,
+                       const int64_t* z, const int32_t* l2g, int32_t n_local, float skin, float* pos_local,
+                       int64_t* z_local, void* stream);
+/* owner -> ghost copy of rows [*, width] (width = F or 3F): push stores this rank's rows into the peers' landing
+ * buffers and raises the flags; wait spins (bounded) on the local flags and copies the landing buffer into
+ * ghost_rows = first ghost row of the same array. */
+NN_API int nn_dd_halo_push(const nn_dd_comm* c, int32_t channel, int32_t seq, const float* rows, int32_t width, void* stream);
+NN_API int nn_dd_halo_wait(const nn_dd_comm* c, int32_t channel, int32_t seq, float* ghost_rows, int32_t width, void* stream);
+/* completes the step: owned forces are written into every rank's complete force array (owner-only writes), the
+ * partial energy [1] / virial [9] / stress [9] and status words into every rank's table; after the flags,
+ * forces_out [n_atoms_total,3], out_small = {energy, virial[9], stress[9]} (fp64 sums in rank order: the same
+ * bits on every rank) and out_status [NN_DD_STATUS_WORDS] (OR over ranks) are written.  virial / stress may be NULL. */
+NN_API int nn_dd_finish(const nn_dd_comm* c, int32_t seq, const float* forces_owned, const int32_t* l2g, const float* energy,
+                        const float* virial, const float* stress, const int32_t* nbr_status, float* forces_out,
+                        float* out_small, int32_t* out_status, void* stream);
 
 /* ------------------------------------------------------------------ training-path primitives (row T)
  * Closed under differentiation together with nn_gemm128 and nn_halo_pack (= gather rows), so autograd can

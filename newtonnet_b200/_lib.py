@@ -18,7 +18,10 @@ NN_WE_IMAGE_FLOATS = 2 * 128 * 32
 ST_EDGE_OVERFLOW, ST_ROW_OVERFLOW, ST_BATCH_UNSORTED, ST_SINGULAR_CELL, ST_N_EDGES, ST_N_PAIRS, ST_N_CELLS = range(7)
 STAGES = ['nbr', 'geom', 'node_gemm', 'pair_gemm', 'message', 'aggregate', 'head', 'bwd_gather', 'bwd_message',
           'bwd_aggregate', 'force', 'other']
-PH_BEGIN, PH_FWD_NODE, PH_FWD_PAIR, PH_HEAD, PH_BWD_SEED, PH_BWD_NODE, PH_BWD_PAIR, PH_FINISH = range(8)
+(PH_BEGIN, PH_FWD_NODE, PH_FWD_PAIR, PH_HEAD, PH_BWD_SEED, PH_BWD_NODE, PH_BWD_PAIR, PH_FINISH, PH_FWD_PAIR_A, PH_FWD_PAIR_B,
+ PH_BWD_NORM, PH_BWD_NODE_B, PH_BWD_PAIR_A, PH_BWD_PAIR_B) = range(14)
+DD_MAX_RANKS, DD_CHANNELS, DD_MAX_WIDTH, DD_PARTIAL, DD_STATUS_WORDS = 16, 2, 384, 32, 8
+DD_ST_STALE, DD_ST_TIMEOUT, DD_ST_OVERFLOW, DD_ST_BAD_INPUT, DD_ST_STEP, DD_ST_EDGES = range(6)
 BUF_MN, BUF_F_OUT, BUF_DFB, BUF_ABAR = range(4)
 PRO_NONE, PRO_SILU, PRO_ROWSCALE3, PRO_SILU_SAVE = 0, 1, 2, 3
 EPI_BIAS, EPI_DSILU, EPI_ADD, EPI_EQUIV_BWD, EPI_MUL = 0, 1, 2, 3, 4
@@ -61,6 +64,17 @@ class GemmChainArgs(C.Structure):
                 ('out', C.c_int32)]
 
 
+class DDComm(C.Structure):
+    _R = DD_MAX_RANKS
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('n_atoms_total', C.c_int32), ('n_owned', C.c_int32),
+                ('n_ghost', C.c_int32), ('pad_', C.c_int32), ('stride', C.c_int32 * DD_CHANNELS),
+                ('landing', (_fp * 2) * DD_CHANNELS), ('flags', _fp * DD_CHANNELS), ('forces_full', _fp), ('partials', _fp),
+                ('peer_landing', ((_fp * DD_MAX_RANKS) * 2) * DD_CHANNELS), ('peer_flags', (_fp * DD_MAX_RANKS) * DD_CHANNELS),
+                ('peer_forces_full', _fp * DD_MAX_RANKS), ('peer_partials', _fp * DD_MAX_RANKS),
+                ('send_idx', _fp), ('send_begin', C.c_int32 * DD_MAX_RANKS), ('send_end', C.c_int32 * DD_MAX_RANKS),
+                ('row_offset', C.c_int32 * DD_MAX_RANKS), ('step', _fp), ('done', _fp), ('status', _fp)]
+
+
 class EvalArgs(C.Structure):
     _fields_ = [('nbr', C.POINTER(Nbr)), ('w', C.POINTER(Weights)), ('z', _fp), ('want_forces', C.c_int32),
                 ('want_virial', C.c_int32), ('n_owned', C.c_int32), ('pad_', C.c_int32), ('energy', _fp), ('forces', _fp), ('virial', _fp), ('stress', _fp),
@@ -92,9 +106,10 @@ SYMBOLS = {
     'nn_p2p_get_handle': (C.c_int, [_fp, _fp]),
     'nn_p2p_open_handle': (C.c_int, [_fp, C.POINTER(C.c_void_p)]),
     'nn_p2p_close_handle': (C.c_int, [_fp]),
-    'nn_halo_push': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
-    'nn_copy_d2d': (C.c_int, [_fp, _fp, C.c_size_t, _fp]),
-    'nn_halo_wait': (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    'nn_dd_begin': (C.c_int, [C.POINTER(DDComm), _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_float, _fp, _fp, _fp]),
+    'nn_dd_halo_push': (C.c_int, [C.POINTER(DDComm), C.c_int32, C.c_int32, _fp, C.c_int32, _fp]),
+    'nn_dd_halo_wait': (C.c_int, [C.POINTER(DDComm), C.c_int32, C.c_int32, _fp, C.c_int32, _fp]),
+    'nn_dd_finish': (C.c_int, [C.POINTER(DDComm), C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),

@@ -275,6 +275,7 @@ int make_ctx(const nn_eval_args* a, void* stream, EvalCtx& c) {
 // One phase of the evaluation.  Node-level work (GEMMs, aggregations, head) runs on the first `No` (owned)
 // atoms, pair-level work on every local pair; between phases a domain-decomposed caller refreshes the
 // ghost rows [No, N) of the buffer named in the comment (single-GPU: No == N, nothing to exchange).
+int run_phase(EvalCtx& c, int phase, int l);
 int run_phase(EvalCtx& c, int phase, int l) {
     const nn_weights& W = *c.W; EvalWs& w = c.w; const nn_nbr* nl = c.nl; cudaStream_t s = c.s;
     const int N = c.N, No = c.No, P = c.P, L = c.L; const int* np_dev = c.np_dev;
@@ -292,6 +293,10 @@ int run_phase(EvalCtx& c, int phase, int l) {
         return g.rc;
     }
     case NN_PH_FWD_PAIR: {   // message, edge MLPs, aggregation, equivariant update (R7)
+        NN_TRY(run_phase(c, NN_PH_FWD_PAIR_A, l));
+        return run_phase(c, NN_PH_FWD_PAIR_B, l);
+    }
+    case NN_PH_FWD_PAIR_A: {
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
@@ -306,6 +311,10 @@ int run_phase(EvalCtx& c, int phase, int l) {
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd_rows(nl, No, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }
+        return 0;
+    }
+    case NN_PH_FWD_PAIR_B: {
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         g.fwd(b.f_out, lw.Wu, b.g, 3 * No, NN_PRO_NONE, NN_EPI_BIAS);
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_OTHER, s); NN_TRY(nn_equiv_update_fwd(a_nxt, b.f_out, b.g, a_cur, No, s)); }
@@ -343,12 +352,24 @@ int run_phase(EvalCtx& c, int phase, int l) {
         return 0;
     }
     case NN_PH_BWD_NODE: {   // dfb = fbar + abar*g + (abar*f_out) @ Wu  (owned)   [then ghosts of: dfb, abar]
+        NN_TRY(run_phase(c, NN_PH_BWD_NORM, l));
+        return run_phase(c, NN_PH_BWD_NODE_B, l);
+    }
+    case NN_PH_BWD_NORM: {
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         if (lw.ln_gamma) NN_TRY(nn_layer_norm_bwd_launch(w.abar, lw.ln_gamma, b.ln_xhat, b.ln_rstd, No, s));
+        return 0;
+    }
+    case NN_PH_BWD_NODE_B: {
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         g.bwd(b.f_out, lw.Wu, w.dfb, 3 * No, NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD, nullptr, w.fbar, w.abar, b.g);
         return g.rc;
     }
     case NN_PH_BWD_PAIR: {
+        NN_TRY(run_phase(c, NN_PH_BWD_PAIR_A, l));
+        return run_phase(c, NN_PH_BWD_PAIR_B, l);
+    }
+    case NN_PH_BWD_PAIR_A: {
         const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
         const bool first = l == 0;
         const float* f_in = first ? nullptr : w.layer[l - 1].f_out;
@@ -358,7 +379,11 @@ int run_phase(EvalCtx& c, int phase, int l) {
         if (!first) {
             g.mlp_bwd(w.e2bar, lw.V2, b.q2, w.e2bar, lw.V1, w.mbar, P, true, np_dev);
         }
-        NN_TRY(g.rc);
+        return g.rc;
+    }
+    case NN_PH_BWD_PAIR_B: {
+        const nn_layer_weights& lw = W.layer[l]; LayerBuf& b = w.layer[l];
+        const bool first = l == 0;
         {
             ProfScope ps(NN_STAGE_BWD_MESSAGE, s);
             float* slot = w.x_bar + (size_t)2 * l * P;      // two partial arrays per layer, summed in k_edge_geom_bwd
@@ -437,7 +462,7 @@ extern "C" int nn_eval_phase(const nn_eval_args* a, int32_t phase, int32_t layer
     EvalCtx c;
     NN_TRY(make_ctx(a, stream, c));
     NN_REQUIRE(layer >= 0 && layer < c.L, "layer out of range");
-    NN_REQUIRE(c.bwd || phase < NN_PH_BWD_SEED, "reverse-sweep phase without want_forces");
+    NN_REQUIRE(c.bwd || phase < NN_PH_BWD_SEED || phase == NN_PH_FWD_PAIR_A || phase == NN_PH_FWD_PAIR_B, "reverse-sweep phase without want_forces");
     NN_TRY(run_phase(c, phase, layer));
     NN_CHECK_LAUNCH("nn_eval_phase");
     return 0;

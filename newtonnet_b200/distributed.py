@@ -161,99 +161,253 @@ class HaloExchange:
                 req.wait()
 
 
-class PeerHaloExchange:
-    """Owner -> ghost copy over NVLink peer memory (csrc/p2p.cu): the pack kernel stores rows directly into
-    the peers' landing buffers and raises per-source flags; the receiver spins on its flags and copies
-    its landing buffer into the ghost tail.  No NCCL call on the data path.  Collective: every rank of
-    the group must construct it (and call `exchange`) in the same order."""
+class PeerArena:
+    """One cudaMalloc arena per rank that every peer maps through CUDA IPC (csrc/p2p.cu): landing buffers of the
+    two exchange channels, flag words, the complete force array, the table of per-rank partial sums.  Collective:
+    every rank of the group constructs it at the same time."""
 
-    MAX_WIDTH = 3 * L.NN_F
-
-    def __init__(self, plan, device, group=None):
+    def __init__(self, plan, n_atoms_total, device, group, strides):
         self.plan, self.group, self.device = plan, group, torch.device(device)
         self.lib = L.load()
         self.rank, self.world = plan.rank, plan.world
-        self.epoch = 0
-        self.send_index = torch.from_numpy(plan.send_index).to(self.device)
-        i32 = dict(dtype=torch.int32, device=self.device)
-        self.done = torch.zeros(1, **i32)
-        self.status = torch.zeros(1, **i32)
-        self.expect = torch.tensor([1 if c > 0 else 0 for c in plan.recv_counts], **i32)
-        nbytes = max(plan.n_ghost, 1) * self.MAX_WIDTH * 4
-        self.local = []
-        for _ in range(3):           # two landing buffers (epoch parity) and the flag array
-            p = C.c_void_p()
-            L.check(self.lib.nn_p2p_alloc(nbytes if len(self.local) < 2 else 4 * max(self.world, 1), C.byref(p)), 'nn_p2p_alloc')
-            self.local.append(p.value)
-        handles = []
-        for p in self.local:
-            h = C.create_string_buffer(64)
-            L.check(self.lib.nn_p2p_get_handle(p, h), 'nn_p2p_get_handle')
-            handles.append(h.raw)
+        if not 2 <= self.world <= L.DD_MAX_RANKS:
+            raise ValueError(f'peer-memory transport supports 2..{L.DD_MAX_RANKS} ranks')
+        al = lambda n: (int(n) + 255) // 256 * 256
+        landing = al(max(plan.n_ghost, 1) * L.DD_MAX_WIDTH * 4)
+        off, cur = {}, 0
+        for ch in range(L.DD_CHANNELS):
+            for par in range(2):
+                off['landing', ch, par] = cur; cur += landing
+        off['forces'] = cur; cur += al(n_atoms_total * 12)
+        off['partials'] = cur; cur += al(self.world * L.DD_PARTIAL * 4)
+        for ch in range(L.DD_CHANNELS):
+            off['flags', ch] = cur; cur += al(self.world * 4)
+        self.nbytes = cur
+        p = C.c_void_p()
+        L.check(self.lib.nn_p2p_alloc(cur, C.byref(p)), 'nn_p2p_alloc')
+        self.base = p.value
+        h = C.create_string_buffer(64)
+        L.check(self.lib.nn_p2p_get_handle(self.base, h), 'nn_p2p_get_handle')
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, handles, group=group)
-        self.peers = [s for s in range(self.world) if s != self.rank and plan.send_counts[s] > 0]
+        dist.all_gather_object(gathered, (h.raw, off), group=group)
         self.opened = {}
         for s in range(self.world):
-            if s == self.rank or (plan.send_counts[s] == 0):
+            if s == self.rank:
                 continue
-            ptrs = []
-            for raw in gathered[s]:
-                q = C.c_void_p()
-                L.check(self.lib.nn_p2p_open_handle(C.create_string_buffer(raw, 64), C.byref(q)), 'nn_p2p_open_handle')
-                ptrs.append(q.value)
-            self.opened[s] = ptrs
-        n = len(self.peers)
-        begins, ends, off = [], [], 0
-        counts_nonself = [(s, plan.send_counts[s]) for s in range(self.world) if s != self.rank]
-        pos = {}
-        for s, c in counts_nonself:      # send_index is ordered by destination rank
-            pos[s] = (off, off + c)
-            off += c
-        self._arrays = []
-        for par in range(2):
-            landing = (C.c_void_p * max(n, 1))(*[self.opened[s][par] for s in self.peers])
-            flags = (C.c_void_p * max(n, 1))(*[self.opened[s][2] for s in self.peers])
-            self._arrays.append((landing, flags))
-        self._row_offset = (C.c_int32 * max(n, 1))(*[plan.send_row_offset[s] for s in self.peers])
-        self._begin = (C.c_int32 * max(n, 1))(*[pos[s][0] for s in self.peers])
-        self._end = (C.c_int32 * max(n, 1))(*[pos[s][1] for s in self.peers])
-        if self.world > 1:
-            dist.barrier(group=group)
-
-    def exchange(self, rows):
-        p = self.plan
-        if p.world == 1:
-            return
-        self.epoch += 1
-        par = self.epoch & 1
-        width = rows.shape[1]
-        s = torch.cuda.current_stream().cuda_stream
-        if self.peers:
-            landing, flags = self._arrays[par]
-            L.check(self.lib.nn_halo_push(rows.data_ptr(), self.send_index.data_ptr(), width, len(self.peers), landing, flags,
-                                          self._row_offset, self._begin, self._end, self.rank, self.epoch,
-                                          self.done.data_ptr(), s), 'nn_halo_push')
-        if p.n_ghost:
-            L.check(self.lib.nn_halo_wait(self.local[2], self.expect.data_ptr(), self.world, self.epoch,
-                                          self.status.data_ptr(), s), 'nn_halo_wait')
-            L.check(self.lib.nn_copy_d2d(rows[p.n_owned:].data_ptr(), self.local[par], p.n_ghost * width * 4, s), 'nn_copy_d2d')
-
-    def check(self):
-        st = int(self.status.item())
-        if st:
-            raise RuntimeError(f'halo exchange timed out waiting for rank {st - 1}')
+            q = C.c_void_p()
+            L.check(self.lib.nn_p2p_open_handle(C.create_string_buffer(gathered[s][0], 64), C.byref(q)), 'nn_p2p_open_handle')
+            self.opened[s] = q.value
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.send_index = torch.from_numpy(plan.send_index).to(self.device)
+        self.step = torch.zeros(1, **i32)
+        self.done = torch.zeros(L.DD_CHANNELS, **i32)
+        self.status = torch.zeros(L.DD_STATUS_WORDS, **i32)
+        c = L.DDComm()
+        c.world, c.rank, c.n_atoms_total = self.world, self.rank, int(n_atoms_total)
+        c.n_owned, c.n_ghost = plan.n_owned, plan.n_ghost
+        for ch in range(L.DD_CHANNELS):
+            c.stride[ch] = int(strides[ch])
+            c.flags[ch] = self.base + off['flags', ch]
+            for par in range(2):
+                c.landing[ch][par] = self.base + off['landing', ch, par]
+        c.forces_full = self.base + off['forces']
+        c.partials = self.base + off['partials']
+        begin = 0
+        for s in range(self.world):
+            c.send_begin[s] = begin
+            begin += plan.send_counts[s]
+            c.send_end[s] = begin
+            c.row_offset[s] = plan.send_row_offset[s]
+            if s == self.rank:
+                continue
+            o = gathered[s][1]
+            for ch in range(L.DD_CHANNELS):
+                c.peer_flags[ch][s] = self.opened[s] + o['flags', ch]
+                for par in range(2):
+                    c.peer_landing[ch][par][s] = self.opened[s] + o['landing', ch, par]
+            c.peer_forces_full[s] = self.opened[s] + o['forces']
+            c.peer_partials[s] = self.opened[s] + o['partials']
+        c.send_idx = self.send_index.data_ptr()
+        c.step, c.done, c.status = self.step.data_ptr(), self.done.data_ptr(), self.status.data_ptr()
+        self.comm = c
+        self.bytes_per_row_exchange = lambda width: 4 * width * int(plan.send_index.shape[0])
+        dist.barrier(group=group)
 
     def close(self):
-        torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier(group=self.group)
-        for ptrs in self.opened.values():
-            for q in ptrs:
-                self.lib.nn_p2p_close_handle(q)
-        for q in self.local:
-            self.lib.nn_p2p_free(q)
-        self.opened, self.local = {}, []
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for q in self.opened.values():
+            self.lib.nn_p2p_close_handle(q)
+        if self.base:
+            self.lib.nn_p2p_free(self.base)
+        self.opened, self.base = {}, None
+
+
+class _PeerStep:
+    """One decomposed evaluation over static buffers: launched eagerly the first time, then captured and replayed
+    as ONE CUDA graph (two streams: halo exchanges off the critical path run on the side stream)."""
+
+    def __init__(self, dd, z, pos, cell3, want_virial):
+        from newtonnet_b200.engine import NeighborList, get_engine
+        self.dd = dd
+        dev = pos.device
+        self.device = dev
+        model = dd.model
+        self.engine = get_engine(dev)
+        self.lib = self.engine.lib
+        self.pack = model._weight_pack(dev)
+        self.want_virial = bool(want_virial)
+        N = pos.shape[0]
+        self.N = N
+        cutoff = self.pack.cutoff
+        plan = HaloPlan(pos.detach().cpu().numpy(), cell3[0].detach().cpu().numpy(), dd.rank, dd.world, cutoff, dd.grid,
+                        skin=dd.skin)
+        self.plan = plan
+        nL = self.pack.n_layers
+        self.strides = (2 * nL + 1, max(2 * nL - 1, 1))
+        self.arena = PeerArena(plan, N, dev, dd.group, self.strides)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.n_local, self.n_owned = len(plan.local_to_global), plan.n_owned
+        self.l2g = torch.from_numpy(plan.local_to_global.astype(np.int32)).to(dev)
+        # static inputs (graph replays read these) and the plan's reference state
+        self.z_in = z.to(torch.int64).contiguous().clone()
+        self.pos_in = pos.detach().to(torch.float32).contiguous().clone()
+        self.cell_in = cell3.detach().to(torch.float32).contiguous().clone()
+        self.pos_ref = self.pos_in.clone()
+        self.cell_ref = self.cell_in.clone()
+        self.z_l = self.z_in[self.l2g.long()].contiguous()
+        self.pos_l = self.pos_in[self.l2g.long()].contiguous()
+        self.batch_l = torch.zeros(self.n_local, dtype=torch.int64, device=dev)
+        # outputs
+        self.energy = torch.zeros(1, **f32); self.forces_l = torch.zeros(max(self.n_owned, 1), 3, **f32)
+        self.virial = torch.zeros(1, 3, 3, **f32); self.stress = torch.zeros(1, 3, 3, **f32)
+        self.forces_out = torch.zeros(N, 3, **f32)
+        self.small = torch.zeros(19, **f32)
+        self.out_status = torch.zeros(L.DD_STATUS_WORDS, dtype=torch.int32, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self.calls = 0
+        self._NeighborList = NeighborList
+        self.nl = None
+        self._size_neighbor_list()
+
+    # ---- capacities
+    def _new_list(self, cap):
+        nl = self._NeighborList(self.engine, self.pos_l, self.cell_in, self.batch_l, cap_edges=cap)
+        nl.struct.n_owned = self.n_owned
+        return nl
+
+    def _size_neighbor_list(self, needed=None):
+        s = torch.cuda.current_stream().cuda_stream
+        if needed is None:
+            probe = self._new_list(0)
+            L.check(self.lib.nn_nbr_count(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_count')
+            needed = probe.check()[L.ST_N_EDGES]
+        cap = int(needed * 1.08) + 64
+        self.nl = self._new_list(cap + cap % 2)
+        nbytes = self.lib.nn_eval_workspace_bytes(self.n_local, 1, self.nl.cap_pairs, self.pack.n_layers, 1)
+        self.ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        a = L.EvalArgs()
+        a.nbr, a.w, a.z = C.pointer(self.nl.struct), C.pointer(self.pack.struct), self.z_l.data_ptr()
+        a.want_forces, a.want_virial, a.n_owned = 1, int(self.want_virial), self.n_owned
+        a.energy, a.forces = self.energy.data_ptr(), self.forces_l.data_ptr()
+        a.virial, a.stress = (self.virial.data_ptr(), self.stress.data_ptr()) if self.want_virial else (None, None)
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        self.args = a
+        self.graph = None
+        self.calls = 0
+
+    # ---- one step on the current stream (+ side stream)
+    def _launch(self):
+        lib, a, comm = self.lib, self.args, C.byref(self.arena.comm)
+        main = torch.cuda.current_stream()
+        side = self.side if self.dd.overlap else main
+        s = main.cuda_stream
+        nL, F = self.pack.n_layers, L.NN_F
+        n_owned = self.n_owned
+        ghost = lambda which, l, width: lib.nn_eval_buffer(C.byref(a), which, l) + n_owned * width * 4
+        rows = lambda which, l: lib.nn_eval_buffer(C.byref(a), which, l)
+
+        def phase(ph, l=0):
+            L.check(lib.nn_eval_phase(C.byref(a), ph, l, s), f'nn_eval_phase({ph},{l})')
+
+        seq = [0, 0]
+
+        def exchange(stream, ch, which, l, width):
+            st = stream.cuda_stream
+            L.check(lib.nn_dd_halo_push(comm, ch, seq[ch], rows(which, l), width, st), 'nn_dd_halo_push')
+            L.check(lib.nn_dd_halo_wait(comm, ch, seq[ch], ghost(which, l, width), width, st), 'nn_dd_halo_wait')
+            seq[ch] += 1
+
+        def fork():          # side stream continues from here
+            if side is not main:
+                side.wait_stream(main)
+
+        def join():
+            if side is not main:
+                main.wait_stream(side)
+
+        L.check(lib.nn_dd_begin(comm, self.pos_in.data_ptr(), self.pos_ref.data_ptr(), self.cell_in.data_ptr(),
+                                self.cell_ref.data_ptr(), self.z_in.data_ptr(), self.l2g.data_ptr(), self.n_local,
+                                self.dd.skin, self.pos_l.data_ptr(), self.z_l.data_ptr(), s), 'nn_dd_begin')
+        L.check(lib.nn_nbr_count(C.byref(self.nl.struct), self.pack.cutoff, s), 'nn_nbr_count')
+        L.check(lib.nn_nbr_fill(C.byref(self.nl.struct), self.pack.cutoff, s), 'nn_nbr_fill')
+        phase(L.PH_BEGIN)
+        pending = False
+        for l in range(nL):
+            phase(L.PH_FWD_NODE, l)
+            exchange(main, 0, L.BUF_MN, l, F)
+            if pending:
+                join(); pending = False
+            phase(L.PH_FWD_PAIR_A, l)
+            if l + 1 < nL:           # f_out(l) is needed by the NEXT layer's pair phase only: exchange it behind FWD_PAIR_B / FWD_NODE
+                fork()
+                exchange(side, 1, L.BUF_F_OUT, l, 3 * F)
+                pending = True
+            phase(L.PH_FWD_PAIR_B, l)
+        phase(L.PH_HEAD)
+        phase(L.PH_BWD_SEED)
+        for l in reversed(range(nL)):
+            phase(L.PH_BWD_NORM, l)
+            fork()                   # abar(l) is final here and needed by BWD_PAIR_B only
+            exchange(side, 1, L.BUF_ABAR, 0, F)
+            phase(L.PH_BWD_NODE_B, l)
+            exchange(main, 0, L.BUF_DFB, 0, 3 * F)
+            phase(L.PH_BWD_PAIR_A, l)
+            join()
+            phase(L.PH_BWD_PAIR_B, l)
+        phase(L.PH_FINISH)
+        assert seq[0] == self.strides[0] - 1 and seq[1] == self.strides[1], (seq, self.strides)
+        L.check(lib.nn_dd_finish(comm, seq[0], self.forces_l.data_ptr(), self.l2g.data_ptr(), self.energy.data_ptr(),
+                                 self.virial.data_ptr() if self.want_virial else None,
+                                 self.stress.data_ptr() if self.want_virial else None, self.nl.status.data_ptr(),
+                                 self.forces_out.data_ptr(), self.small.data_ptr(), self.out_status.data_ptr(), s), 'nn_dd_finish')
+
+    def run(self, z, pos, cell3):
+        self.z_in.copy_(z, non_blocking=True)
+        self.pos_in.copy_(pos.detach(), non_blocking=True)
+        self.cell_in.copy_(cell3.detach(), non_blocking=True)
+        self.calls += 1
+        if self.calls == 1 or not self.dd.use_cuda_graph:
+            self._launch()
+            return
+        if self.graph is None:
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+        self.graph.replay()
+
+    def halo_bytes_per_step(self):
+        """Bytes this rank stores into peer memory per step (feature rows + forces), and the number of exchanges."""
+        F, nL = L.NN_F, self.pack.n_layers
+        n_send = int(self.plan.send_index.shape[0])
+        rows = n_send * 4 * F * (nL + 3 * (nL - 1) + nL + 3 * nL)
+        return rows + (self.plan.world - 1) * self.n_owned * 12, self.strides[0] + self.strides[1]
+
+    def close(self):
+        self.graph = None
+        self.arena.close()
 
 
 class DomainDecomposition:
@@ -263,21 +417,92 @@ class DomainDecomposition:
     -> CustomOutputSet with energy [1], gradient_force [N,3] (complete on every rank), stress, virial.
     """
 
-    def __init__(self, model, group=None, grid=None, skin=1.0, transport='p2p'):
+    def __init__(self, model, group=None, grid=None, skin=1.0, transport='p2p', overlap=True, use_cuda_graph=True):
         """skin (A): the brick/ghost plan is kept while no atom has moved more than skin/2 since it was
         made (the ghost shell is cutoff + skin thick); the neighbour list itself is rebuilt every call.
-        transport: 'p2p' = pack kernel storing into peer memory over NVLink (csrc/p2p.cu), 'nccl' =
-        pack kernel + all_to_all_single."""
+        transport: 'p2p' = the whole step is one CUDA graph, halo rows and results travel as stores into peer
+        memory over NVLink (csrc/p2p.cu); 'nccl' = eager phases, pack kernel + all_to_all_single + all-reduce.
+        overlap: exchange f_out / abar rows on a second stream behind the node-level work."""
         self.model, self.group, self.grid, self.skin = model, group, grid, float(skin)
         self.transport = transport
+        self.overlap, self.use_cuda_graph = bool(overlap), bool(use_cuda_graph)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.plan = None
         self._ws = None
         self._nl = None
         self._state = None
+        self._peer = None
         self.n_plans = 0
 
+    # ------------------------------------------------------------------ peer-memory path (CUDA graph)
+    def _use_peer(self):
+        return self.transport == 'p2p' and self.world > 1 and dist.get_backend(self.group) == 'nccl'
+
+    def check(self):
+        """Read the status of the last step (one small D2H copy, synchronises).  Returns the status words;
+        raises on conditions that invalidate the result.  `__call__(..., sync=True)` does this itself."""
+        st = self._peer.out_status.cpu().tolist()
+        if st[L.DD_ST_TIMEOUT]:
+            raise RuntimeError('halo exchange timed out waiting for a peer rank')
+        if st[L.DD_ST_BAD_INPUT]:
+            self._peer.nl.check()
+            raise RuntimeError('neighbour list failure on a peer rank (degree overflow / singular cell)')
+        if st[L.DD_ST_STALE]:
+            raise RuntimeError('an atom moved more than skin/2 since the brick/ghost plan was made and the step ran with '
+                               'sync=False: call with sync=True (replans automatically) or increase skin')
+        if st[L.DD_ST_OVERFLOW]:
+            raise RuntimeError('neighbour-list capacity overflow in a step run with sync=False')
+        return st
+
+    def _call_peer(self, z, pos, cell, want_virial, sync):
+        from newtonnet_b200.models.output import CustomOutputSet
+        cell3 = cell.reshape(-1, 3, 3)
+        N = pos.shape[0]
+        for attempt in range(4):
+            p = self._peer
+            if p is None or p.N != N or p.want_virial != bool(want_virial):
+                if p is not None:
+                    p.close()
+                p = self._peer = _PeerStep(self, z, pos, cell3, want_virial)
+                self.plan = p.plan
+                self.n_plans += 1
+            p.run(z, pos, cell3)
+            if not sync:
+                break
+            st = p.out_status.cpu().tolist()            # the one host synchronisation of the step
+            if st[L.DD_ST_TIMEOUT]:
+                raise RuntimeError('halo exchange timed out waiting for a peer rank')
+            if st[L.DD_ST_BAD_INPUT]:
+                p.nl.check()
+                raise RuntimeError('neighbour list failure on a peer rank (degree overflow / singular cell)')
+            if st[L.DD_ST_STALE]:                        # same decision on every rank: the flags were OR-ed by nn_dd_finish
+                p.close()
+                self._peer = None
+                continue
+            if st[L.DD_ST_OVERFLOW]:
+                need = p.nl.status.cpu().tolist()
+                p._size_neighbor_list(max(need[L.ST_EDGE_OVERFLOW], need[L.ST_N_EDGES]))
+                continue
+            break
+        else:
+            raise RuntimeError('domain decomposition did not converge (plan / capacity kept changing)')
+        dt = pos.dtype
+        out = CustomOutputSet(z=z, pos=pos, cell=cell, batch=torch.zeros(N, dtype=torch.int64, device=pos.device))
+        small = p.small.clone()
+        out.energy = small[:1].to(dt)
+        out.gradient_force = p.forces_out.clone().to(dt)
+        out.virial = small[1:10].reshape(1, 3, 3).to(dt)
+        out.stress = small[10:19].reshape(1, 3, 3).to(dt)
+        out.n_owned, out.n_ghost = p.n_owned, p.plan.n_ghost
+        return out
+
+    def close(self):
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+
+    # ------------------------------------------------------------------ eager path (NCCL / gloo collectives)
     def _workspace(self, nbytes, device):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=device)
@@ -293,16 +518,22 @@ class DomainDecomposition:
         self.plan = plan
         self.n_plans += 1
         l2g = torch.from_numpy(plan.local_to_global).to(dev)
-        if self._state is not None and hasattr(self._state['halo'], 'close'):
-            self._state['halo'].close()
-        use_p2p = self.transport == 'p2p' and self.world > 1 and dist.get_backend(self.group) == 'nccl'
-        halo = PeerHaloExchange(plan, dev, self.group) if use_p2p else HaloExchange(plan, dev, self.group)
+        halo = HaloExchange(plan, dev, self.group)
         self._state = dict(l2g=l2g, halo=halo, pos_ref=pos.detach().clone(),
                            z_l=z.to(torch.int64)[l2g].contiguous(), n=pos.shape[0],
                            batch_l=torch.zeros(len(plan.local_to_global), dtype=torch.int64, device=dev))
         self._nl = None
 
-    def __call__(self, z, pos, cell, want_virial=True):
+    def __call__(self, z, pos, cell, want_virial=True, sync=True):
+        """sync=False (peer-memory transport only): no host synchronisation at all - the caller checks a batch of
+        steps afterwards with `check()`; a stale plan or a capacity overflow then raises instead of being repaired."""
+        if self._use_peer():
+            if cell.reshape(-1, 3, 3).shape[0] != 1:
+                raise ValueError('DomainDecomposition evaluates one periodic system')
+            return self._call_peer(z, pos, cell, want_virial, sync)
+        return self._call_eager(z, pos, cell, want_virial)
+
+    def _call_eager(self, z, pos, cell, want_virial=True):
         from newtonnet_b200.engine import NeighborList, _stream, get_engine
         from newtonnet_b200.models.output import CustomOutputSet
         model = self.model
@@ -405,11 +636,9 @@ class DomainDecomposition:
         tail = buf[3 * N:].cpu()                                  # the one host synchronisation of the step
         red = tail[:19].double() + tail[19:38].double()
         status = nl.check()
-        if hasattr(halo, 'check'):
-            halo.check()
         if float(tail[38]) > 0:      # some rank's list outgrew its capacity: resize everywhere and repeat
             self._nl = None
-            return self.__call__(z, pos, cell, want_virial)
+            return self._call_eager(z, pos, cell, want_virial)
         dt = pos.dtype
         out = CustomOutputSet(z=z, pos=pos, cell=cell, batch=torch.zeros(N, dtype=torch.int64, device=dev))
         red = red.to(dev)

@@ -42,16 +42,44 @@ def _dd_worker(rank, world, port, nside, out_path, transport='p2p'):
         t = lambda a: torch.tensor(a, device=dev)
         model = _model(dev, ['energy', 'gradient_force', 'stress', 'virial'])
         dd = DomainDecomposition(model, transport=transport)
-        out = dd(t(z), t(pos), t(cell))
-        out2 = dd(t(z), t(pos), t(cell))                 # second call reuses capacities
-        assert torch.equal(out.gradient_force, out2.gradient_force)
+        out = dd(t(z), t(pos), t(cell))                  # eager first step (plan, capacities)
+        out2 = dd(t(z), t(pos), t(cell))                 # captured as one CUDA graph and replayed (peer transport)
+        out3 = dd(t(z), t(pos), t(cell))                 # replay
+        assert torch.equal(out.gradient_force, out2.gradient_force) and torch.equal(out.gradient_force, out3.gradient_force)
+        assert torch.equal(out.energy, out3.energy) and torch.equal(out.stress, out3.stress)
+        extra = {}
+        if transport == 'p2p':
+            # no-sync steps on new positions, checked afterwards; then a large move (> skin / 2) forces a replan
+            rng = np.random.default_rng(5)
+            pos_b = (pos + rng.normal(0, 0.02, pos.shape)).astype(np.float32)
+            ob = dd(t(z), t(pos_b), t(cell), sync=False)
+            st = dd.check()
+            assert dd.n_plans == 1 and st[0] == 0
+            pos_c = pos_b.copy()
+            pos_c[::97] += np.float32(0.7)
+            oc = dd(t(z), t(pos_c), t(cell))
+            assert dd.n_plans == 2
+            od = dd(t(z), t(pos_c), t(cell))             # graph of the new plan
+            assert torch.equal(oc.gradient_force, od.gradient_force)
+            # the same evaluation without the second stream / without the graph gives the same bits
+            dd2 = DomainDecomposition(model, transport=transport, overlap=False, use_cuda_graph=False)
+            oe = dd2(t(z), t(pos_c), t(cell))
+            assert torch.equal(oe.gradient_force, oc.gradient_force) and torch.equal(oe.energy, oc.energy)
+            dd2.close()
+            extra = dict(fb=ob.gradient_force.cpu().numpy(), eb=ob.energy.cpu().numpy(), fc=oc.gradient_force.cpu().numpy(),
+                         ec=oc.energy.cpu().numpy(), pos_b=pos_b, pos_c=pos_c)
         if rank == 0:
             ref = model(t(z), t(pos), t(cell), t(batch))
+            for key, p_ in (('b', extra.get('pos_b')), ('c', extra.get('pos_c'))):
+                if p_ is not None:
+                    r = model(t(z), t(p_), t(cell), t(batch))
+                    extra['rf' + key] = r.gradient_force.cpu().numpy(); extra['re' + key] = r.energy.cpu().numpy()
             np.savez(out_path, e=out.energy.cpu().numpy(), f=out.gradient_force.cpu().numpy(),
                      s=out.stress.cpu().numpy(), v=out.virial.cpu().numpy(), re=ref.energy.cpu().numpy(),
                      rf=ref.gradient_force.cpu().numpy(), rs=ref.stress.cpu().numpy(), rv=ref.virial.cpu().numpy(),
-                     n_owned=out.n_owned, n_ghost=out.n_ghost)
+                     n_owned=out.n_owned, n_ghost=out.n_ghost, z=z, pos=pos, cell=cell, batch=batch, **extra)
         dist.barrier(device_ids=[rank])
+        dd.close()
     finally:
         dist.destroy_process_group()
 
@@ -70,6 +98,16 @@ def test_domain_decomposition_matches_single_gpu(world, transport, tmp_path):
     assert np.abs(d['s'] - d['rs']).max() < 1e-4 * np.abs(d['rs']).max()
     assert np.abs(d['v'] - d['rv']).max() < 1e-4 * np.abs(d['rv']).max()
     assert d['n_ghost'] > 0
+    if transport == 'p2p':
+        for key in 'bc':
+            assert np.abs(d['f' + key] - d['rf' + key]).max() < 2e-5
+            assert abs(d['e' + key][0] - d['re' + key][0]) <= 1e-5 * abs(d['re' + key][0])
+    # ... and the oracle (fp64, reference algorithm) on the same box: the north-star tolerances
+    from oracle import newtonnet_oracle as O
+    w = load_weights('seed0')
+    ref = O.forward(w, d['z'], d['pos'], d['cell'], d['batch'], dtype=torch.float64, stress=True)
+    assert abs(d['e'][0] - ref['energy'][0]) <= 1e-5 * abs(ref['energy'][0])
+    assert np.abs(d['f'] - ref['forces']).max() < 1e-4
 
 
 def _dp_worker(rank, world, port, out_dir):
