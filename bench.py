@@ -686,7 +686,7 @@ def main_b200(args):
     if world == 1 and args.gpus > 1:       # convenience: relaunch under torchrun
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', '29511', os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
+        return subprocess.call(cmd, stdout=_REAL_STDOUT)     # the children write the JSON line to the real stdout
     import torch
     import torch.distributed as dist
     ctx = Ctx(args)
@@ -740,6 +740,8 @@ def main_b200(args):
         dist.destroy_process_group()
     return 0
 
+
+_REAL_STDOUT = None
 
 if __name__ == '__main__':
     # stdout carries exactly one JSON line: anything a library prints there (e.g. NCCL's version banner)

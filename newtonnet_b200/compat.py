@@ -10,7 +10,9 @@ from the state dict, so old layouts load too: the shipped MD17 checkpoint
 """
 import contextlib
 import importlib
+import pickle
 import sys
+import types
 
 import torch
 
@@ -34,17 +36,46 @@ _LEGACY_KEYS = {
 
 @contextlib.contextmanager
 def reference_class_aliases():
-    """Make `newtonnet.*` importable as this package while unpickling (no-op if the real one is loaded)."""
+    """Make `newtonnet.*` importable as this package while unpickling (no-op if a `newtonnet` package - the real one
+    or this repo's shim - is already loaded or importable)."""
     added = []
     if 'newtonnet' not in sys.modules:
-        for ref, ours in _ALIASES.items():
-            sys.modules[ref] = importlib.import_module(ours)
-            added.append(ref)
+        try:
+            importlib.import_module('newtonnet.models.newtonnet')
+        except ImportError:
+            for ref in [m for m in sys.modules if m == 'newtonnet' or m.startswith('newtonnet.')]:
+                sys.modules.pop(ref, None)           # a half-imported package must not shadow the aliases
+            for ref, ours in _ALIASES.items():
+                sys.modules[ref] = importlib.import_module(ours)
+                added.append(ref)
     try:
         yield
     finally:
         for ref in added:
             sys.modules.pop(ref, None)
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    """Whole-module pickles of the current reference contain a `les.Les` instance (and its submodules) inside
+    aggregators.N (models/output.py:229); `les` is an un-vendored dependency.  Classes of packages that are not on the
+    hot path and cannot be imported resolve to inert nn.Module stand-ins - `convert_state_dict` drops aggregators.*."""
+    _SKIPPABLE = ('les', 'torch_geometric', 'wandb')
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            if module.split('.')[0] in self._SKIPPABLE:
+                return type(name, (torch.nn.Module,), {'__module__': module, '_newtonnet_b200_stub': True})
+            raise
+
+
+def _tolerant_pickle_module():
+    m = types.ModuleType('newtonnet_b200_tolerant_pickle')
+    m.__dict__.update({k: v for k, v in pickle.__dict__.items() if not k.startswith('__')})
+    m.Unpickler = _TolerantUnpickler
+    m.load = lambda f, **kw: _TolerantUnpickler(f, **kw).load()
+    return m
 
 
 def convert_state_dict(sd):
@@ -71,7 +102,20 @@ def _find_cutoff(obj, default=5.0):
     return default
 
 
-def model_from_state_dict(sd, output_properties=None, cutoff=5.0):
+def _activation_name(obj):
+    """Name of the activation of a pickled reference module (layers/activations.py:5-31), read off the module tree."""
+    act = None
+    try:
+        act = obj.interaction_layers[0].message_nodepart[1]
+    except (AttributeError, IndexError, TypeError):
+        return None
+    name = type(act).__name__
+    return {'SiLU': 'swish', 'ReLU': 'relu', 'GELU': 'gelu', 'Tanh': 'tanh', 'Softplus': 'ssp', 'ShiftedSoftplus': 'ssp'}.get(name, name)
+
+
+def model_from_state_dict(sd, output_properties=None, cutoff=5.0, activation='swish'):
+    """activation: the reference's activation key; a state dict does not record it, so callers that know it pass it.
+    Anything but swish / silu raises (the kernels implement SiLU) instead of silently evaluating the wrong function."""
     from newtonnet_b200.models.newtonnet import NewtonNet
     sd = convert_state_dict(sd)
     emb = sd['embedding_layers.node_embedding.weight']
@@ -82,7 +126,7 @@ def model_from_state_dict(sd, output_properties=None, cutoff=5.0):
     if output_properties is None:
         output_properties = ['energy', 'gradient_force']
     model = NewtonNet(cutoff=cutoff, n_features=n_features, n_basis=n_basis, n_interactions=n_int,
-                      activation='swish', layer_norm=layer_norm, output_properties=list(output_properties))
+                      activation=activation, layer_norm=layer_norm, output_properties=list(output_properties))
     model = model.to(emb.dtype)
     model.load_state_dict(sd, strict=True)
     return model
@@ -94,7 +138,7 @@ def load_model(path_or_obj, map_location=None):
     obj = path_or_obj
     if isinstance(obj, (str, bytes)) or hasattr(obj, 'read') or hasattr(obj, '__fspath__'):
         with reference_class_aliases():
-            obj = torch.load(obj, map_location=map_location, weights_only=False)
+            obj = torch.load(obj, map_location=map_location, weights_only=False, pickle_module=_tolerant_pickle_module())
     if isinstance(obj, dict) and 'model_state_dict' in obj:
         obj = obj['model_state_dict']       # train_state.pt layout (trainer.py:242-251)
     if isinstance(obj, dict):
@@ -107,7 +151,8 @@ def load_model(path_or_obj, map_location=None):
             props = getattr(obj, 'infer_properties', None)
         # bypass NewtonNet.state_dict() of half-initialised mirror objects: walk the raw module tree
         sd = torch.nn.Module.state_dict(obj)
-        model = model_from_state_dict(sd, output_properties=props, cutoff=_find_cutoff(obj))
+        act = _activation_name(obj)
+        model = model_from_state_dict(sd, output_properties=props, cutoff=_find_cutoff(obj), activation=act or 'swish')
     else:
         raise TypeError(f'cannot build a NewtonNet from {type(obj)}')
     if map_location is not None:

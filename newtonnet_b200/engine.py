@@ -239,6 +239,18 @@ class Engine:
     def grow(self, nl, cutoff, needed):
         return self._build_with_capacity(nl.pos, nl.cell, nl.batch, cutoff, needed)
 
+    def checked_neighbor_list(self, pos, cell, batch, cutoff):
+        """neighbor_list + status read; a cached list whose capacity the new positions outgrow is rebuilt larger
+        (the sync-free `neighbor_list` leaves that to the caller).  Returns a list that is complete."""
+        nl = self.neighbor_list(pos, cell, batch, cutoff)
+        st = nl.check()
+        if st[L.ST_EDGE_OVERFLOW]:
+            nl = self.grow(nl, cutoff, max(st[L.ST_EDGE_OVERFLOW], st[L.ST_N_EDGES]))
+            st = nl.check()
+            if st[L.ST_EDGE_OVERFLOW]:
+                raise RuntimeError('neighbour list capacity overflow after regrow')
+        return nl
+
     # ------------------------------------------------------------------ evaluation
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != self.device:

@@ -26,8 +26,7 @@ class RadiusGraph(nn.Module):
             batch = torch.zeros(pos.shape[0], dtype=torch.long, device=pos.device)
         if cell is None:
             cell = torch.zeros(int(batch.max().item()) + 1 if batch.numel() else 1, 3, 3, device=pos.device)
-        nl = get_engine(pos.device).neighbor_list(pos, cell, batch, float(self.r))
-        nl.check()
+        nl = get_engine(pos.device).checked_neighbor_list(pos, cell, batch, float(self.r))
         ei = nl.edge_index()
         ep = nl.edge_pair[:nl.n_edges].long()
         sign = torch.where(ep < 0, -1.0, 1.0).to(torch.float32).unsqueeze(1)

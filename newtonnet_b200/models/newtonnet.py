@@ -97,7 +97,10 @@ class NewtonNet(nn.Module):
         for key in props:
             if key not in _SUPPORTED:
                 raise NotImplementedError(f"output '{key}' is outside the B200 energy/force/stress path")
-        if 'hessian' in props or any(getattr(layer, 'create_graph', False) for layer in self.output_layers):
+        # training (reference train/trainer.py:303-313 differentiates the loss w.r.t. the parameters, also for energy-only
+        # or direct_force-only heads, train/loss.py): outputs must carry a grad_fn -> autograd-composable path
+        trainable = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if 'hessian' in props or trainable or any(getattr(layer, 'create_graph', False) for layer in self.output_layers):
             from newtonnet_b200.train import differentiable_forward
             return differentiable_forward(self, z, pos, cell, batch)
         if not pos.is_cuda:

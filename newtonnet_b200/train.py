@@ -241,7 +241,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
         pos.requires_grad = True
     # ---- edges (reference order) from the cell-list kernel; image shifts are constants of the graph
     static = static_nl is not None
-    nl = static_nl if static else get_engine(dev).neighbor_list(pos, cell, batch, cutoff)
+    nl = static_nl if static else get_engine(dev).checked_neighbor_list(pos, cell, batch, cutoff)   # regrows on overflow
     ei, dst, src, disp, valid = _edges(nl, pos, N, static)
     if static:
         pad = torch.cat([torch.full((1, 1), float(cutoff), dtype=torch.float32, device=dev),
@@ -313,18 +313,28 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
 
 
 # ----------------------------------------------------------------------------- training step (config 5)
-def allreduce_gradients(params, group=None):
+def allreduce_gradients(params, group=None, flags=None):
     """Data-parallel gradient averaging: ONE all-reduce of a flat fp32 bucket (401,155 floats = 1.6 MB for
     the default model) instead of one per tensor; missing gradients (the dead layer-0 equiv_message2,
-    the frozen frequencies) travel as zeros so every rank reduces the same layout."""
+    the frozen frequencies) travel as zeros so every rank reduces the same layout.
+    flags: optional 1-D float tensor of per-rank condition flags appended to the bucket; on return it holds their
+    SUM over ranks (so every rank takes the same decision on a condition raised by one of them)."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return None
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params]
+    n_flags = 0 if flags is None else flags.numel()
+    if n_flags:
+        parts.append(flags.reshape(-1).to(parts[0].dtype))
+    flat = torch.cat(parts)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:
         dist.all_reduce(flat, group=group)
+        if n_flags:
+            flags.copy_(flat[-n_flags:].reshape(flags.shape))
         flat /= world
+    if n_flags:
+        flat = flat[:-n_flags]
     off = 0
     for p in params:
         n = p.numel()
@@ -364,7 +374,7 @@ class GraphedTrainingStep:
     and loss.backward() are captured once, every later call copies the batch into the static buffers and replays.
     Gradient all-reduce, clipping and the optimizer step stay outside the graph (a handful of launches).  Non-periodic
     batches use the exact bound sum n_b (n_b - 1) as edge capacity; periodic ones probe and add headroom, and a replay
-    that overflowed raises (rebuild the object with a larger `cap_edges`)."""
+    that overflowed raises before the optimizer step (rebuild the object with a larger `cap_edges`)."""
 
     def __init__(self, model, optimizer, z, pos, cell, batch, e_target, f_target, force_weight=50.0, clip_grad=1.0,
                  group=None, cap_edges=None):
@@ -419,7 +429,15 @@ class GraphedTrainingStep:
         self.e_target.copy_(e_target); self.f_target.copy_(f_target)
         self.graph.replay()
         self.replays += 1
-        allreduce_gradients(self.model.parameters(), self.group)
+        # a batch that outgrew the captured edge capacity leaves stale rows in the replayed graph: the flag travels with
+        # the gradient bucket so that every rank sees it, and it is read (one small D2H copy) BEFORE the optimizer moves
+        flag = (self.nl.status[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).to(torch.float32)
+        allreduce_gradients(self.model.parameters(), self.group, flags=flag)
+        if float(flag.item()) > 0:
+            self.optimizer.zero_grad(set_to_none=True)
+            need = int(self.nl.status[L.ST_EDGE_OVERFLOW].item())
+            raise RuntimeError(f'edge capacity {self.nl.cap_edges} of the captured training graph overflowed on some rank '
+                               f'(this rank needs {need}): the step was NOT applied; rebuild GraphedTrainingStep with a larger cap_edges')
         if self.clip_grad and self.clip_grad > 0:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_grad)
         self.optimizer.step()

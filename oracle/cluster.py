@@ -13,8 +13,10 @@ def oracle_cluster_forces(z, pos, cell, sd, center, r_dest=1.5, n_layers=3, cuto
     """Forces of the destination atoms within r_dest of atom `center` from the CPU oracle (cell-list edge set +
     hand-derived reverse sweep, fp64) on a non-periodic cluster cut out of the periodic box: the force on an atom
     depends on atoms within 2 * n_layers * cutoff of it, so the cluster radius is r_dest + 2 * n_layers * cutoff + margin."""
+    import os
     import torch
     from oracle import newtonnet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
     Ld = np.diag(cell[0]).astype(np.float64)
     d = pos.astype(np.float64) - pos[center].astype(np.float64)
     d -= Ld * np.rint(d / Ld)

@@ -546,3 +546,74 @@ def test_hessian_through_the_calculator(tmp_path):
     assert h.shape == (21, 3, 21, 3)
     assert np.abs(h - d['hessian']).max() < 2e-3 and np.abs(d['hessian']).max() > 50
     assert np.abs(calc.results['forces'] - d['forces']).max() < F_ATOL
+
+
+def test_training_path_regrows_neighbour_capacity():
+    """Same atom count, denser second batch through the differentiable (training) path and through RadiusGraph: the
+    cached edge capacity overflows and must be regrown, not truncated (round-1 advisor finding)."""
+    from newtonnet_b200.layers.representations import RadiusGraph
+    from oracle import newtonnet_oracle as O
+    model = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    model.train()
+    z, pos, cell, batch = O.water_box(5)
+    t = lambda a: torch.tensor(a, device=dev())
+    o1 = model(t(z), t(pos).requires_grad_(True), t(cell), t(batch))
+    pos2 = (pos * 0.8).astype(np.float32); cell2 = (cell * 0.8).astype(np.float32)
+    ei, _ = O.radius_graph_cell_list(pos2, cell2, batch)
+    p2 = t(pos2).requires_grad_(True)
+    o2 = model(t(z), p2, t(cell2), t(batch))
+    assert o2.edge_index.shape[1] == ei.shape[1] > 1.5 * o1.edge_index.shape[1]
+    (o2.energy.sum() + o2.gradient_force.square().sum()).backward()
+    ref = O.forward(load_weights('seed0'), z, pos2, cell2, batch, dtype=torch.float64)
+    assert np.abs(o2.gradient_force.detach().cpu().double().numpy() - ref['forces']).max() < F_ATOL
+    rg = RadiusGraph(5.0)
+    rg(t(pos), t(cell), t(batch))
+    e2, d2 = rg(t(pos2), t(cell2), t(batch))
+    assert np.array_equal(e2.cpu().numpy(), ei) and d2.shape[0] == ei.shape[1]
+
+
+def test_graphed_training_step_refuses_overflowing_batch():
+    """A replay whose batch outgrew the captured edge capacity must raise BEFORE the optimizer moves (advisor finding)."""
+    from newtonnet_b200.train import GraphedTrainingStep
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.water_box(4)
+    rng = np.random.default_rng(0)
+    t = lambda a, dt=None: torch.tensor(a, device=dev(), dtype=dt)
+    args = (t(z), t(pos), t(cell), t(batch), t(rng.standard_normal(1), torch.float32), t(rng.standard_normal(pos.shape), torch.float32))
+    model = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    step = GraphedTrainingStep(model, opt, *args)
+    step(*args)
+    before = [p.detach().clone() for p in model.parameters()]
+    dense = (args[0], t((pos * 0.7).astype(np.float32)), t((cell * 0.7).astype(np.float32))) + args[3:]
+    with pytest.raises(RuntimeError, match='overflow'):
+        step(*dense)
+    assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+
+
+def test_reference_module_pickle_evaluates_like_the_reference():
+    """Whole-module pickle of the current reference (with its les.Les aggregator member) -> load_model -> CUDA path;
+    outputs against the reference's own outputs saved next to the pickle (tests/golden/make_pickle_golden.py)."""
+    from newtonnet_b200.compat import load_model
+    d = np.load(f'{GOLDEN}/ref_module_pickle.npz')
+    model = load_model(f'{GOLDEN}/ref_module_pickle.pt', map_location=dev())
+    model.eval()
+    n = len(d['z'])
+    out = model(torch.tensor(d['z'], device=dev()), torch.tensor(d['pos'], device=dev()), torch.zeros(1, 3, 3, device=dev()),
+                torch.zeros(n, dtype=torch.long, device=dev()))
+    assert abs(out.energy.item() - d['energy'][0]) <= 1e-5 * abs(d['energy'][0]) + 1e-5
+    assert np.abs(out.gradient_force.cpu().numpy() - d['forces']).max() < F_ATOL
+
+
+def test_training_mode_energy_only_head_gets_gradients():
+    """model.train() with output_properties=['energy'] (trainable in the reference, train/loss.py) must produce outputs
+    with a grad_fn (advisor finding: the inference path returned constants)."""
+    model = make_model(load_weights('seed0'), ['energy'])
+    model.train()
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.molecule_batch(4, seed=3)
+    t = lambda a: torch.tensor(a, device=dev())
+    out = model(t(z), t(pos), t(cell), t(batch))
+    assert out.energy.grad_fn is not None
+    out.energy.sum().backward()
+    assert model.interaction_layers[0].message_nodepart[0].weight.grad is not None

@@ -106,3 +106,79 @@ def test_pickled_mirror_module_round_trip(tmp_path):
     torch.save(m.state_dict(), p)
     m3 = load_model(str(p), map_location='cpu')
     assert set(m3.state_dict()) == set(w)
+
+
+def test_struct_layout_of_dd_comm_matches_header(tmp_path):
+    """nn_dd_comm is filled from Python: its ctypes mirror must have the C compiler's size and field offsets."""
+    import ctypes as C
+    import subprocess
+    from newtonnet_b200 import _lib
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", '
+                   'sizeof(nn_dd_comm), offsetof(nn_dd_comm, landing), offsetof(nn_dd_comm, peer_landing), offsetof(nn_dd_comm, send_idx), '
+                   'offsetof(nn_dd_comm, step), offsetof(nn_dd_comm, peer_flags));return 0;}\n' % os.path.join(ROOT, 'include', 'newtonnet_b200.h'))
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', str(src), '-o', str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    D = _lib.DDComm
+    assert got == [C.sizeof(D), D.landing.offset, D.peer_landing.offset, D.send_idx.offset, D.step.offset, D.peer_flags.offset]
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """The `newtonnet` shim: reference-side import lines work unchanged (scripts/simulate.py:6, scripts/newtonnet_train.py:9,
+    utils/ase_interface.py:8-13) and resolve to the CUDA-backed classes."""
+    import importlib
+    import newtonnet_b200
+    nn_pkg = importlib.import_module('newtonnet')
+    assert getattr(nn_pkg, '__backend__', None) == 'newtonnet_b200', 'a different `newtonnet` package shadows the shim'
+    from newtonnet.models import NewtonNet
+    from newtonnet.models.newtonnet import EmbeddingNet, InteractionNet
+    from newtonnet.models.output import DerivativeProperty, SecondDerivativeProperty, get_aggregator_by_string, get_output_by_string
+    from newtonnet.layers.precision import get_precision_by_string
+    from newtonnet.layers.scalers import get_scaler_by_string, set_scaler_by_string, ScaleShift
+    from newtonnet.layers.representations import EdgeEmbedding
+    from newtonnet.data import RadiusGraph
+    from newtonnet.utils.ase_interface import MLAseCalculator
+    from newtonnet.utils.pretrained_models import download_checkpoint
+    assert NewtonNet is newtonnet_b200.models.NewtonNet
+    assert MLAseCalculator is importlib.import_module('newtonnet_b200.utils.ase_interface').MLAseCalculator
+    m = NewtonNet(output_properties=['energy', 'gradient_force'])
+    assert type(m).__module__ == 'newtonnet_b200.models.newtonnet' and isinstance(m.embedding_layers, EmbeddingNet)
+    with pytest.raises(ImportError):
+        from newtonnet.data import MolecularDataset   # noqa: F401
+
+
+def test_whole_module_pickle_of_current_reference_loads_without_les():
+    """Pickle written by the unmodified reference (tests/golden/make_pickle_golden.py): class paths newtonnet.* and a
+    `les.Les` instance inside aggregators.0 - `les` is not installed here (advisor finding, round 1)."""
+    import importlib.util
+    from newtonnet_b200.compat import load_model
+    from newtonnet_b200.models import NewtonNet
+    assert importlib.util.find_spec('les') is None
+    model = load_model(os.path.join(GOLDEN, 'ref_module_pickle.pt'), map_location='cpu')
+    assert isinstance(model, NewtonNet) and model.output_properties == ['energy', 'gradient_force']
+    assert len(model.interaction_layers) == 1
+    sd = model.state_dict()
+    assert not any(k.startswith('aggregators.') for k in sd)
+    assert all(torch.isfinite(v).all() for v in sd.values())
+    assert float(sd['scalers.0.shift.weight'].abs().sum()) > 0      # the randomised scaler made it through
+
+
+def test_activation_of_a_pickled_module_is_not_silently_replaced():
+    from newtonnet_b200.compat import _activation_name, load_model
+    from newtonnet_b200.models import NewtonNet
+    m = NewtonNet(output_properties=['energy'])
+    assert _activation_name(m) == 'swish'
+    for layer in m.interaction_layers:
+        layer.message_nodepart[1] = torch.nn.ReLU()
+    with pytest.raises(NotImplementedError):
+        load_model(_as_plain_module(m))
+
+
+def _as_plain_module(m):
+    """A torch.nn.Module that is not this package's NewtonNet but has its module tree (like a reference pickle)."""
+    class Foreign(torch.nn.Module):
+        pass
+    f = Foreign()
+    f.__dict__.update(m.__dict__)
+    return f
