@@ -97,13 +97,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Per-system description written by the neighbour-list planner and reused by the virial kernel.
 struct SysMeta {
-    int mode;          // 0 = not periodic, 1 = diagonal cell, 2 = general cell (one grid cell, all pairs)
+    int mode;          // 0 = not periodic, 1 = diagonal cell, 2 = general cell
     int nc[3];         // grid dimensions
     int cell_off;      // first global grid cell of this system
     int first, count;  // atom range
-    int pad_;
-    float lo[3];       // grid origin (mode 0)
-    float wsc[3];      // cells per unit length (mode 0) / cells per unit fractional coordinate (mode 1)
+    int nimg;          // mode 2: lattice images n in [-nimg, nimg]^3 are enumerated; -1 = one grid cell, all pairs
+    float lo[3];       // grid origin (modes 0 and 2: Cartesian grid over the bounding box of the atoms)
+    float wsc[3];      // cells per unit length (modes 0, 2) / cells per unit fractional coordinate (mode 1)
     float L[3];        // diagonal cell lengths (mode 1)
     float H[9];        // cell, row-major (mode 2)
     float Hinv[9];     // (cell^T)^-1, row-major (mode 2)

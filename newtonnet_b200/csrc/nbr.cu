@@ -98,7 +98,7 @@ __global__ void k_sys_bounds(const float* __restrict__ pos, const int* __restric
 // One block: periodic flag over the whole batch (reference: `not (cell == 0).all()`,
 // representations.py:86 - if ANY entry of ANY cell is non-zero every system takes the solve path),
 // then per-system mode / grid, then an exclusive scan of the grid sizes.
-__global__ void k_sys_plan(const float* __restrict__ cell, const int* __restrict__ sys_ptr,
+__global__ void __launch_bounds__(1024) k_sys_plan(const float* __restrict__ cell, const int* __restrict__ sys_ptr,
                            const float* __restrict__ bounds, int B, float cutoff, SysMeta* __restrict__ meta,
                            int* __restrict__ status) {
     __shared__ int s_any;
@@ -116,7 +116,7 @@ __global__ void k_sys_plan(const float* __restrict__ cell, const int* __restrict
         int ncells = 0;
         SysMeta m;
         if (b < B) {
-            m.first = sys_ptr[b]; m.count = sys_ptr[b + 1] - sys_ptr[b]; m.pad_ = 0;
+            m.first = sys_ptr[b]; m.count = sys_ptr[b + 1] - sys_ptr[b]; m.nimg = 0;
             const float* h = cell + 9 * b;
             float lo[3] = {bounds[6 * b], bounds[6 * b + 1], bounds[6 * b + 2]};
             float hi[3] = {bounds[6 * b + 3], bounds[6 * b + 4], bounds[6 * b + 5]};
@@ -148,7 +148,26 @@ __global__ void k_sys_plan(const float* __restrict__ cell, const int* __restrict
                     C[3] = -(H[1] * H[8] - H[2] * H[7]); C[4] = (H[0] * H[8] - H[2] * H[6]); C[5] = -(H[0] * H[7] - H[1] * H[6]);
                     C[6] = (H[1] * H[5] - H[2] * H[4]); C[7] = -(H[0] * H[5] - H[2] * H[3]); C[8] = (H[0] * H[4] - H[1] * H[3]);
                     for (int k = 0; k < 9; ++k) m.Hinv[k] = (float)(C[k] * inv);
-                    ext[0] = ext[1] = ext[2] = 0.0;   // single grid cell: all pairs of the system
+                    // The reference keeps ONE image per ordered pair, n = round((cell^T)^-1 d), and tests |d - cell n| < r_c
+                    // (its `cell @ n` quirk), i.e. atom j passes iff it lies within r_c of the point p_i - cell n.  So the
+                    // candidates of atom i are the atoms near the query points p_i - cell n for every image n that can occur,
+                    // found in a NON-periodic Cartesian grid over the atoms' bounding box; a hit counts only if the reference
+                    // formula returns this very n (each pair has exactly one).  |n_a| <= sum_k |Hinv[a][k]| * extent_k.
+                    double nmax = 0.0, hsum = 0.0;
+                    for (int a = 0; a < 3; ++a) {
+                        double bnd = 0.0;
+                        for (int k = 0; k < 3; ++k) bnd += fabs(C[3 * a + k] * inv) * fmax((double)hi[k] - (double)lo[k], 0.0);
+                        nmax = fmax(nmax, bnd);
+                    }
+                    for (int k = 0; k < 9; ++k) hsum += fabs(H[k]);
+                    if (det != 0.0 && nmax < 2.49) {
+                        m.nimg = (int)floor(nmax + 0.501);        // margin: fp32 rounding of (cell^T)^-1 d next to a half-integer
+                        wmin += 64.0 * 1.1920929e-7 * (hsum * (m.nimg + 1) + (double)amax);    // fp32 rounding of p_i - cell n
+                        for (int d = 0; d < 3; ++d) { ext[d] = fmax((double)hi[d] - (double)lo[d], 1e-6); m.lo[d] = lo[d]; }
+                    } else {
+                        m.nimg = -1;                  // unwrapped input far outside the cell: single grid cell, all pairs
+                        ext[0] = ext[1] = ext[2] = 0.0;
+                    }
                 }
             }
             long long cap = 2LL * m.count; if (cap < 1) cap = 1;
@@ -166,7 +185,7 @@ __global__ void k_sys_plan(const float* __restrict__ cell, const int* __restrict
             }
             for (int d = 0; d < 3; ++d) {
                 m.nc[d] = nc[d];
-                m.wsc[d] = (m.mode == 0) ? (float)((double)nc[d] / ext[d]) : (float)nc[d];
+                m.wsc[d] = (m.mode == 0 || (m.mode == 2 && m.nimg >= 0)) ? (float)((double)nc[d] / ext[d]) : (float)nc[d];
             }
             ncells = nc[0] * nc[1] * nc[2];
         }
@@ -192,7 +211,7 @@ __device__ __forceinline__ void cell_coords(const SysMeta& m, float x, float y, 
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         int v = 0;
-        if (m.mode == 0) {
+        if (m.mode == 0 || (m.mode == 2 && m.nimg >= 0)) {
             v = (int)(((double)p[d] - (double)m.lo[d]) * (double)m.wsc[d]);
         } else if (m.mode == 1) {
             double f = (double)p[d] / (double)m.L[d];
@@ -225,6 +244,35 @@ __global__ void k_bin_fill(int N, const int* __restrict__ atom_cell, const int* 
     sorted_atoms[cell_start[cid] + slot] = i;   // order inside a cell is irrelevant: rows are sorted later
 }
 
+// Candidates of one grid cell: every lane tests one atom j with the reference's arithmetic.  IMG >= 0: general cell, the
+// hit counts only when the reference's own image vector equals the enumerated one (img_x/y/z).
+template <bool FILL, bool IMG>
+__device__ __forceinline__ void scan_cell(int i, int lane, const float3 pi, const float* __restrict__ pos, const SysMeta& m,
+                                          int s0, int s1, const int* __restrict__ sorted_atoms, float cutoff, int n_owned,
+                                          float img_x, float img_y, float img_z, int* __restrict__ row_buf, int& found) {
+    for (int s = s0 + lane; s - lane < s1; s += 32) {
+        bool pass = false;
+        int j = -1;
+        if (s < s1) {
+            j = sorted_atoms[s];
+            if (j != i && (i < n_owned || j < n_owned)) {   // ghost-ghost pairs belong to other ranks
+                float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]),
+                                       __fsub_rn(pi.z, pos[3 * j + 2]));
+                float3 n3;
+                d = nn_min_image(d, m, &n3);
+                pass = nn_norm3(d) < cutoff;
+                if (IMG) pass = pass && n3.x == img_x && n3.y == img_y && n3.z == img_z;
+            }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (FILL && pass) {
+            int slot = found + __popc(mask & ((1u << lane) - 1u));
+            if (slot < NN_MAX_DEGREE) row_buf[slot] = j;
+        }
+        found += __popc(mask);
+    }
+}
+
 // Visit every candidate neighbour of atom i once; FILL = false counts, FILL = true collects into smem.
 template <bool FILL>
 __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __restrict__ pos,
@@ -232,9 +280,47 @@ __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __
                                                 const int* __restrict__ sorted_atoms, float cutoff,
                                                 int n_owned, int* __restrict__ row_buf) {
     const float3 pi = make_float3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    int found = 0;
+    if (m.mode == 2 && m.nimg >= 0) {
+        // general cell: query points q = p_i - cell n in the Cartesian grid (see k_sys_plan)
+        const int R = m.nimg;
+        for (int nx = -R; nx <= R; ++nx)
+            for (int ny = -R; ny <= R; ++ny)
+                for (int nz = -R; nz <= R; ++nz) {
+                    const float fx = (float)nx, fy = (float)ny, fz = (float)nz;
+                    const double q[3] = {(double)pi.x - ((double)m.H[0] * fx + (double)m.H[1] * fy + (double)m.H[2] * fz),
+                                         (double)pi.y - ((double)m.H[3] * fx + (double)m.H[4] * fy + (double)m.H[5] * fz),
+                                         (double)pi.z - ((double)m.H[6] * fx + (double)m.H[7] * fy + (double)m.H[8] * fz)};
+                    int c[3];
+                    bool out = false;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const double v = floor((q[d] - (double)m.lo[d]) * (double)m.wsc[d]);
+                        if (v < -1.0 || v > (double)m.nc[d]) out = true;          // no cell within one cell of q
+                        c[d] = out ? 0 : (int)v;
+                        // atoms on the upper face of the bounding box are binned into the last cell (clamped)
+                    }
+                    if (out) continue;
+                    for (int ox = -1; ox <= 1; ++ox) {
+                        const int cx = c[0] + ox;
+                        if (cx < 0 || cx >= m.nc[0]) continue;
+                        for (int oy = -1; oy <= 1; ++oy) {
+                            const int cy = c[1] + oy;
+                            if (cy < 0 || cy >= m.nc[1]) continue;
+                            for (int oz = -1; oz <= 1; ++oz) {
+                                const int cz = c[2] + oz;
+                                if (cz < 0 || cz >= m.nc[2]) continue;
+                                const int cid = m.cell_off + (cx * m.nc[1] + cy) * m.nc[2] + cz;
+                                scan_cell<FILL, true>(i, lane, pi, pos, m, cell_start[cid], cell_start[cid + 1], sorted_atoms, cutoff,
+                                                      n_owned, fx, fy, fz, row_buf, found);
+                            }
+                        }
+                    }
+                }
+        return found;
+    }
     int c[3];
     cell_coords(m, pi.x, pi.y, pi.z, c);
-    int found = 0;
     const bool per = m.mode != 0;
     for (int ox = -1; ox <= 1; ++ox) {
         int cx = c[0] + ox;
@@ -249,26 +335,8 @@ __device__ __forceinline__ int visit_neighbours(int i, int lane, const float* __
                 if (per) { if ((m.nc[2] == 1 && oz != 0) || (m.nc[2] == 2 && oz < 0)) continue; cz = (cz + m.nc[2]) % m.nc[2]; }
                 else if (cz < 0 || cz >= m.nc[2]) continue;
                 int cid = m.cell_off + (cx * m.nc[1] + cy) * m.nc[2] + cz;
-                int s0 = cell_start[cid], s1 = cell_start[cid + 1];
-                for (int s = s0 + lane; s - lane < s1; s += 32) {
-                    bool pass = false;
-                    int j = -1;
-                    if (s < s1) {
-                        j = sorted_atoms[s];
-                        if (j != i && (i < n_owned || j < n_owned)) {   // ghost-ghost pairs belong to other ranks
-                            float3 d = make_float3(__fsub_rn(pi.x, pos[3 * j]), __fsub_rn(pi.y, pos[3 * j + 1]),
-                                                   __fsub_rn(pi.z, pos[3 * j + 2]));
-                            d = nn_min_image(d, m, nullptr);
-                            pass = nn_norm3(d) < cutoff;
-                        }
-                    }
-                    unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    if (FILL && pass) {
-                        int slot = found + __popc(mask & ((1u << lane) - 1u));
-                        if (slot < NN_MAX_DEGREE) row_buf[slot] = j;
-                    }
-                    found += __popc(mask);
-                }
+                scan_cell<FILL, false>(i, lane, pi, pos, m, cell_start[cid], cell_start[cid + 1], sorted_atoms, cutoff, n_owned,
+                                       0.f, 0.f, 0.f, row_buf, found);
             }
         }
     }
@@ -283,6 +351,7 @@ k_nbr_count(const float* __restrict__ pos, const int64_t* __restrict__ batch, in
     int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (i >= N) return;
+    if (i >= n_owned) return;      // ghost rows stay empty: every consumer walks the rows of OWNED atoms only (deg is zero-filled)
     SysMeta m = meta[batch[i]];
     int found = visit_neighbours<false>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, n_owned, nullptr);
     if (lane == 0) {
@@ -295,8 +364,16 @@ __global__ void k_finish_count(const int* __restrict__ row_ptr, int N, int cap_e
     int E = row_ptr[N];
     status[NN_ST_N_EDGES] = E;
     // on overflow the pair arrays are not (re)written: expose zero pairs so no kernel reads stale entries
-    status[NN_ST_N_PAIRS] = E > cap_edges ? 0 : E / 2;
+    status[NN_ST_N_PAIRS] = 0;               // set by k_finish_pairs once the pair table exists
     if (E > cap_edges) status[NN_ST_EDGE_OVERFLOW] = E;
+}
+// P = number of forward pairs = E / 2 for a complete (symmetric) list; with empty ghost rows (domain decomposition) an
+// owned-ghost pair has ONE directed edge, so P = E_owned-owned / 2 + E_owned-ghost.
+__global__ void k_finish_pairs(const int* __restrict__ pair_ptr, int N, int cap_pairs, int* __restrict__ status) {
+    const int P = pair_ptr[N];
+    if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
+    if (P > cap_pairs) { status[NN_ST_EDGE_OVERFLOW] = max(2 * P, status[NN_ST_N_EDGES] + 2); return; }
+    status[NN_ST_N_PAIRS] = P;
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -308,7 +385,7 @@ k_nbr_fill(const float* __restrict__ pos, const int64_t* __restrict__ batch, int
     if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int i = blockIdx.x * kWarpsPerBlock + w;
-    if (i >= N) return;
+    if (i >= N || i >= n_owned) return;      // ghost rows: no edges, no forward pairs (fwd_cnt is zero-filled)
     SysMeta m = meta[batch[i]];
     int* buf = s_rows[w];
     int found = visit_neighbours<true>(i, lane, pos, m, cell_start, sorted_atoms, cutoff, n_owned, buf);
@@ -413,14 +490,17 @@ extern "C" int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream) {
     k_sys_ptr<<<nn_ceil_div(N + 1, 256), 256, 0, s>>>(nl->batch, N, B, nl->sys_ptr, nl->status); NN_LAUNCHED(1);
     k_sys_bounds<<<B, 128, 0, s>>>(nl->pos, nl->sys_ptr, w.bounds); NN_LAUNCHED(1);
     k_sys_plan<<<1, 1024, 0, s>>>(nl->cell, nl->sys_ptr, w.bounds, B, cutoff, w.meta, nl->status); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_nbr_count(plan)");      // the library scans below clear a pending launch error
     if (N > 0) {
         k_bin_count<<<nn_ceil_div(N, 256), 256, 0, s>>>(nl->pos, nl->batch, N, w.meta, w.atom_cell, w.cell_count); NN_LAUNCHED(1);
+        NN_CHECK_LAUNCH("nn_nbr_count(bin)");
         size_t tb = w.scan_tmp_bytes;
         cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.cell_count, w.cell_start, cap_cells + 1, s); NN_LAUNCHED(2);
         k_bin_fill<<<nn_ceil_div(N, 256), 256, 0, s>>>(N, w.atom_cell, w.cell_start, w.cell_fill, w.sorted_atoms); NN_LAUNCHED(1);
         k_nbr_count<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
             nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->n_owned > 0 ? nl->n_owned : N, w.deg,
             nl->status); NN_LAUNCHED(1);
+        NN_CHECK_LAUNCH("nn_nbr_count(count)");
     }
     size_t tb = w.scan_tmp_bytes;
     cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.deg, nl->row_ptr, N + 1, s); NN_LAUNCHED(2);
@@ -441,9 +521,11 @@ extern "C" int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream) {
             nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->n_owned > 0 ? nl->n_owned : N,
             nl->row_ptr, nl->cap_edges,
             nl->col, w.fwd_cnt, nl->status); NN_LAUNCHED(1);
+        NN_CHECK_LAUNCH("nn_nbr_fill(fill)");
     }
     size_t tb = w.scan_tmp_bytes;
     cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.fwd_cnt, nl->pair_ptr, N + 1, s); NN_LAUNCHED(2);
+    k_finish_pairs<<<1, 1, 0, s>>>(nl->pair_ptr, N, nl->cap_pairs, nl->status); NN_LAUNCHED(1);
     if (N > 0) {
         k_pair_build<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
             nl->pos, nl->batch, N, w.meta, nl->row_ptr, nl->col, nl->pair_ptr, nl->cap_pairs, nl->edge_pair,

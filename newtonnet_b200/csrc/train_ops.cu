@@ -110,12 +110,21 @@ extern "C" int nn_segment_sum(const float* src, const int32_t* perm, const int32
     return 0;
 }
 
-extern "C" size_t nn_gemm128_tn_workspace_bytes(int32_t m) { return (size_t)tn_blocks(m) * 128 * 128 * sizeof(float); }
+int nn_gemm_tn_tc_ctas(int m);
+int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, cudaStream_t s);
+extern "C" int nn_get_gemm_backend(void);
+
+// workspace = one [128,128] partial per block / CTA of whichever back-end runs (the larger of the two counts)
+extern "C" size_t nn_gemm128_tn_workspace_bytes(int32_t m) {
+    const int a = tn_blocks(m), b = nn_gemm_tn_tc_ctas(m);
+    return (size_t)(a > b ? a : b) * 128 * 128 * sizeof(float);
+}
 
 extern "C" int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream) {
     NN_REQUIRE(X && Y && out && workspace, "null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     if (m <= 0) { cudaMemsetAsync(out, 0, 128 * 128 * sizeof(float), s); return 0; }
+    if (nn_get_gemm_backend() >= 1) return nn_gemm_tn_tc_launch(X, Y, m, out, workspace, s);     // tcgen05 3xTF32 (gemm_tn_tc.cu)
     const int nb = tn_blocks(m);
     int rows_per_block = nn_ceil_div(m, nb);
     rows_per_block = nn_ceil_div(rows_per_block, TN_ROWS) * TN_ROWS;

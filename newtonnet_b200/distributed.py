@@ -292,19 +292,25 @@ class _PeerStep:
         self._size_neighbor_list()
 
     # ---- capacities
-    def _new_list(self, cap):
-        nl = self._NeighborList(self.engine, self.pos_l, self.cell_in, self.batch_l, cap_edges=cap)
+    def _new_list(self, cap_edges, cap_pairs):
+        nl = self._NeighborList(self.engine, self.pos_l, self.cell_in, self.batch_l, cap_edges=cap_edges, cap_pairs=cap_pairs)
         nl.struct.n_owned = self.n_owned
         return nl
 
     def _size_neighbor_list(self, needed=None):
+        """Probe: count (-> directed edges of the owned rows), then a trial fill with room for one pair per edge (ghost rows
+        are empty, so an owned-ghost pair has a single directed edge and P lies between E / 2 and E) -> final capacities."""
         s = torch.cuda.current_stream().cuda_stream
-        if needed is None:
-            probe = self._new_list(0)
-            L.check(self.lib.nn_nbr_count(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_count')
-            needed = probe.check()[L.ST_N_EDGES]
-        cap = int(needed * 1.08) + 64
-        self.nl = self._new_list(cap + cap % 2)
+        probe = self._new_list(0, 0)
+        L.check(self.lib.nn_nbr_count(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_count')
+        n_edges = max(probe.check()[L.ST_N_EDGES], int(needed or 0))
+        probe = self._new_list(n_edges + 2, n_edges + 2)
+        L.check(self.lib.nn_nbr_count(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_count')
+        L.check(self.lib.nn_nbr_fill(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_fill')
+        st = probe.check()
+        cap = int(st[L.ST_N_EDGES] * 1.08) + 64
+        self.nl = self._new_list(cap + cap % 2, int(st[L.ST_N_PAIRS] * 1.08) + 64)
+        del probe
         nbytes = self.lib.nn_eval_workspace_bytes(self.n_local, 1, self.nl.cap_pairs, self.pack.n_layers, 1)
         self.ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         a = L.EvalArgs()

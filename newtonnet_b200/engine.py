@@ -116,14 +116,16 @@ class WeightPack:
 class NeighborList:
     """Destination-sorted CSR + undirected pair list on the device (nn_nbr)."""
 
-    def __init__(self, engine, pos, cell, batch, cap_edges):
+    def __init__(self, engine, pos, cell, batch, cap_edges, cap_pairs=None):
+        """cap_pairs: capacity of the pair table; default cap_edges / 2 (complete lists have P = E / 2 - lists with empty
+        ghost rows, domain decomposition, have up to P = E pairs and pass it explicitly)."""
         N, B = pos.shape[0], cell.shape[0]
         dev = pos.device
         i32 = dict(dtype=torch.int32, device=dev)
         self.pos, self.cell, self.batch = pos, cell, batch
         self.n_atoms, self.n_systems = N, B
         self.cap_edges = int(cap_edges)
-        self.cap_pairs = (self.cap_edges + 1) // 2
+        self.cap_pairs = (self.cap_edges + 1) // 2 if cap_pairs is None else int(cap_pairs)
         self.sys_ptr = torch.empty(B + 1, **i32)
         self.row_ptr = torch.empty(N + 1, **i32)
         self.pair_ptr = torch.empty(N + 1, **i32)

@@ -205,7 +205,10 @@ def _edges(nl, pos, N, static):
         E = nl.cap_edges
         ei = torch.zeros(2, E, dtype=torch.int64, device=pos.device)
         L.check(L.load().nn_nbr_edge_index(C.byref(nl.struct), ei.data_ptr(), E, _stream()), 'nn_nbr_edge_index')
-        valid = torch.arange(E, device=pos.device) < nl.status[L.ST_N_EDGES]
+        # a list that outgrew its capacity was not (re)written: expose NO valid rows (the step then computes exact zeros from
+        # padding instead of indexing with stale / uninitialised entries) - the caller reads the overflow flag afterwards
+        n_valid = torch.where(nl.status[L.ST_EDGE_OVERFLOW] != 0, torch.zeros_like(nl.status[L.ST_N_EDGES]), nl.status[L.ST_N_EDGES])
+        valid = torch.arange(E, device=pos.device) < n_valid
         dst = torch.where(valid, ei[0], N - 1)
         src = torch.where(valid, ei[1], N - 1)
         ep = torch.where(valid, nl.edge_pair[:E].long(), 0)
@@ -408,8 +411,10 @@ class GraphedTrainingStep:
         torch.cuda.synchronize(dev)
         optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
+        self.lib.nn_launch_count(1)
         with torch.cuda.graph(self.graph):
             self.loss = self._forward_backward()
+        self.kernels_per_replay = int(self.lib.nn_launch_count(0))      # this library's kernels recorded in the graph
         self.replays = 0
 
     def _forward_backward(self):

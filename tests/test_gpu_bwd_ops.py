@@ -154,3 +154,29 @@ def test_node_aggregate_bwd():
         if not first:
             want_f = dfb.double().clone().index_add_(0, k, dfb.double()[i] * e2.double()[pair][:, None, :])
             torch.testing.assert_close(fbar.double(), want_f, **TOL)
+
+
+@pytest.mark.parametrize('m', [1, 31, 32, 100, 4097, 30230, 200001])
+def test_gemm128_tn_tensor_core(m):
+    """X^T Y (weight gradients) on the tensor cores, 3xTF32, against fp64; row counts around the 32-row K block and the
+    per-CTA row split; deterministic (fixed partition, fixed-order reduction)."""
+    import ctypes as C
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(m)
+    X = torch.randn(m, 128, generator=g).to(dev)
+    Y = torch.randn(m, 128, generator=g).to(dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        out = torch.empty(128, 128, device=dev)
+        ws = torch.empty(lib.nn_gemm128_tn_workspace_bytes(m), dtype=torch.uint8, device=dev)
+        L.check(lib.nn_gemm128_tn(X.data_ptr(), Y.data_ptr(), m, out.data_ptr(), ws.data_ptr(), s), 'nn_gemm128_tn')
+        return out
+    a, b = run(), run()
+    assert torch.equal(a, b)
+    ref = X.double().t() @ Y.double()
+    scale = float(ref.abs().max())
+    # fp32 accumulation over m rows (TMEM accumulator per CTA, then a fixed-order sum of the partials)
+    assert float((a.double() - ref).abs().max()) / scale < 2e-6 * max(1.0, (m / 4096) ** 0.5)

@@ -617,3 +617,38 @@ def test_training_mode_energy_only_head_gets_gradients():
     assert out.energy.grad_fn is not None
     out.energy.sum().backward()
     assert model.interaction_layers[0].message_nodepart[0].weight.grad is not None
+
+
+@pytest.mark.parametrize('kind', ['tilted', 'strongly_tilted', 'unwrapped', 'far_outside', 'symmetric', 'batch_of_two'])
+def test_general_cells_grid_search_matches_dense_reference_search(kind):
+    """Non-diagonal cells are searched through a Cartesian grid + lattice-image enumeration (csrc/nbr.cu, mode 2) instead of
+    all pairs; the result must equal the reference's dense search (layers/representations.py:86-98, incl. its `cell @ n`
+    shift): same edges in the same order, displacements equal to fp32 rounding (the reference solves with LAPACK, here an
+    fp32 inverse - SURVEY 8a R2 'unpinned')."""
+    from newtonnet_b200.layers.representations import RadiusGraph
+    from oracle import newtonnet_oracle as O
+    rng = np.random.default_rng({'tilted': 1, 'strongly_tilted': 2, 'unwrapped': 3, 'far_outside': 4, 'symmetric': 5, 'batch_of_two': 6}[kind])
+    def system(n, L, tilt):
+        cell = np.diag(L).astype(np.float64)
+        cell[1, 0], cell[2, 0], cell[2, 1] = tilt
+        if kind == 'symmetric':
+            cell = cell + np.tril(cell, -1).T
+        frac = rng.random((n, 3))
+        if kind == 'unwrapped':
+            frac += rng.integers(-1, 2, (n, 3))
+        if kind == 'far_outside':
+            frac += rng.integers(-4, 5, (n, 3))
+        return (frac @ cell).astype(np.float32), cell.astype(np.float32)
+    tilt = {'tilted': (2.0, -1.5, 3.0), 'strongly_tilted': (7.0, 6.0, -8.0)}.get(kind, (1.5, 2.5, -2.0))
+    if kind == 'batch_of_two':
+        p1, c1 = system(150, (13.0, 15.0, 14.0), tilt)
+        p2, c2 = system(90, (16.0, 11.0, 12.0), (0.0, 0.0, 0.0))
+        pos, cell, batch = np.concatenate([p1, p2]), np.stack([c1, c2]), np.concatenate([np.zeros(150, np.int64), np.ones(90, np.int64)])
+    else:
+        pos, c, = system(260, (16.0, 14.0, 18.0), tilt)
+        cell, batch = c[None], np.zeros(260, np.int64)
+    ei, disp = RadiusGraph(5.0)(torch.tensor(pos, device=dev()), torch.tensor(cell, device=dev()), torch.tensor(batch, device=dev()))
+    ref_ei, ref_d = O.radius_graph_dense(torch.tensor(pos), torch.tensor(cell), torch.tensor(batch))
+    assert ref_ei.shape[1] > 1000
+    assert np.array_equal(ei.cpu().numpy(), ref_ei.numpy())
+    assert np.abs(disp.cpu().numpy() - ref_d.numpy()).max() < 2e-5
