@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 int nn_gemm128_simt_launch(const nn_gemm_args& a, cudaStream_t s);
+int nn_sum_slices(int n_atoms, int n_systems);
 int nn_gemm128_tc_launch(const nn_gemm_args& a, cudaStream_t s);
 int nn_gemm128_ts_launch(const nn_gemm_args& a, cudaStream_t s);
 int nn_embed_launch(const int64_t* z, const float* emb, float* a, int N, int* status, cudaStream_t s);
@@ -53,6 +54,12 @@ static bool chain_enabled() {          // two-CTA chained GEMM pairs (gemm_chain
 bool nn_pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("NN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+bool nn_pdl_all_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NN_PDL_ALL"); v = (e && e[0] == '1' && nn_pdl_enabled()) ? 1 : 0; }
     return v == 1;
 }
 
@@ -142,10 +149,11 @@ struct EvalWs {
     float *e2bar, *mbar;                  // [P,F]
     float *x_bar, *ubar, *G;              // [2L][P] (dE/dx partial slots), [P,3], [P,3]
     float *vir_atom;                      // [N,9]
+    double *sum_part; int slices;         // [B, slices, 9] partial per-system sums (two-level energy / virial sums)
     size_t total;
 };
 
-EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
+EvalWs carve_eval(void* base, size_t cap, int N, int B, int P, int L, bool bwd) {
     WsCarver c(base, cap);
     EvalWs w{};
     const size_t NF = (size_t)N * kF, PF = (size_t)P * kF;
@@ -162,6 +170,8 @@ EvalWs carve_eval(void* base, size_t cap, int N, int P, int L, bool bwd) {
     w.drbf = bwd ? c.take<float>((size_t)P * kNB) : nullptr;
     w.h1pre = c.take<float>(NF); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
     w.d1 = c.take<float>(NF); w.d2 = c.take<float>(NF);
+    w.slices = nn_sum_slices(N, B);
+    w.sum_part = c.take<double>((size_t)(B > 0 ? B : 1) * w.slices * 9);
     if (bwd) {
         w.abar = c.take<float>(NF); w.mnbar = c.take<float>(NF); w.tmpN = c.take<float>(NF);
         w.fbar = c.take<float>(3 * NF); w.dfb = c.take<float>(3 * NF);
@@ -230,9 +240,8 @@ struct Gemm {
 
 extern "C" size_t nn_eval_workspace_bytes(int32_t n_atoms, int32_t n_systems, int32_t cap_pairs, int32_t n_layers,
                                           int32_t want_forces) {
-    (void)n_systems;
     if (n_layers < 1 || n_layers > NN_MAX_LAYERS) return 0;
-    return carve_eval(nullptr, 0, n_atoms, cap_pairs, n_layers, want_forces != 0).total;
+    return carve_eval(nullptr, 0, n_atoms, n_systems, cap_pairs, n_layers, want_forces != 0).total;
 }
 
 #define NN_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
@@ -242,9 +251,10 @@ int nn_node_aggregate_fwd_rows(const nn_nbr* nl, int n_rows, const float* msg, c
                                bool first, cudaStream_t s);
 int nn_energy_head_fwd_rows(const float* h2pre, const float* w3, const float* b3, const float* scale, const float* shift,
                             const int64_t* z, const int32_t* sys_ptr, int n_rows, int n_systems, float* e_atom,
-                            float* energy, cudaStream_t s);
+                            float* energy, double* partial, int slices, cudaStream_t s);
 int nn_force_virial_rows(const nn_nbr* nl, int n_rows, const float* disp_bar, float* forces, float* virial, float* stress,
-                         void* workspace, cudaStream_t s);
+                         void* workspace, double* partial, int slices, cudaStream_t s);
+int nn_sum_slices(int n_atoms, int n_systems);
 
 namespace {
 
@@ -265,7 +275,7 @@ int make_ctx(const nn_eval_args* a, void* stream, EvalCtx& c) {
     NN_REQUIRE(!a->want_virial || a->virial, "virial buffer required");
     NN_REQUIRE(a->workspace_bytes >= nn_eval_workspace_bytes(c.N, c.B, c.P, c.L, c.bwd), "workspace too small");
     c.s = (cudaStream_t)stream;
-    c.w = carve_eval(a->workspace, a->workspace_bytes, c.N, c.P, c.L, c.bwd);
+    c.w = carve_eval(a->workspace, a->workspace_bytes, c.N, c.B, c.P, c.L, c.bwd);
     c.np_dev = c.nl->status + NN_ST_N_PAIRS;
     // with a reverse sweep the activation GEMMs leave silu'(pre) behind in place of pre
     c.PRO_ACT = c.bwd ? NN_PRO_SILU_SAVE : NN_PRO_SILU;
@@ -327,7 +337,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
     case NN_PH_HEAD: {       // energy head (R8, R9): partial energies over owned atoms
         g.mlp_fwd(a_cur, W.H1, W.hb1, w.h1pre, W.H2, W.hb2, w.h2pre, No, c.PRO_ACT);
         NN_TRY(g.rc);
-        { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd_rows(w.h2pre, W.w3, W.hb3, W.scale, W.shift, c.a->z, nl->sys_ptr, No, c.B, w.e_atom, c.a->energy, s)); }
+        { ProfScope ps(NN_STAGE_HEAD, s); NN_TRY(nn_energy_head_fwd_rows(w.h2pre, W.w3, W.hb3, W.scale, W.shift, c.a->z, nl->sys_ptr, No, c.B, w.e_atom, c.a->energy, w.sum_part, w.slices, s)); }
         if (c.a->direct_force) {   // direct_force head (models/output.py:115-132): no reverse sweep involved
             NN_REQUIRE(W.dscale != nullptr, "direct_force requested but the weights carry no direct_force head");
             g.fwd(a_cur, W.D1, w.d1, No, NN_PRO_NONE, NN_EPI_BIAS, W.db1);
@@ -399,7 +409,7 @@ int run_phase(EvalCtx& c, int phase, int l) {
         { ProfScope ps(NN_STAGE_GEOM, s); NN_TRY(nn_edge_geom_bwd(w.x_bar, 2 * L, w.ubar, w.unit, w.dist, W.cutoff, np_dev, P, w.G, s)); }
         ProfScope ps(NN_STAGE_FORCE, s);
         NN_TRY(nn_force_virial_rows(nl, No, w.G, c.a->forces, c.a->want_virial ? c.a->virial : nullptr,
-                                    c.a->want_virial ? c.a->stress : nullptr, w.vir_atom, s));
+                                    c.a->want_virial ? c.a->stress : nullptr, w.vir_atom, w.sum_part, w.slices, s));
         return 0;
     }
     }
