@@ -182,6 +182,8 @@ k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row
             const float sx = __shfl_sync(0xffffffffu, ux, t), sy = __shfl_sync(0xffffffffu, uy, t),
                         sz = __shfl_sync(0xffffffffu, uz, t);
             const size_t po = (size_t)p * kF + 4 * lane;
+            // (pair rows through L1 on purpose: the atoms of a block share pairs; L1::no_allocate loads were measured at
+            //  +25 % kernel time on c2 and c4)
             am = f4_add(am, ld4(msg + po));
             float4 v1 = ld4(e1 + po);
             fx = f4_fma(sx, v1, fx); fy = f4_fma(sy, v1, fy); fz = f4_fma(sz, v1, fz);
@@ -376,8 +378,11 @@ __global__ void k_energy_head_seed(const float* __restrict__ h2pre, const float*
 // ---------------------------------------------------------------------------- reverse sweep, pair side
 // w[c] = dfb_i[c] - dfb_j[c];  e1bar = sum_c w[c] u[c] (overwrites e1);  ubar[c] += <w[c], e1>;
 // e2bar = sum_c dfb_i[c] * f_in_j[c] + dfb_j[c] * f_in_i[c]
+#ifndef NN_GATHER_BLOCKS
+#define NN_GATHER_BLOCKS 1      // 3 blocks (85 registers) measured: no change
+#endif
 template <bool FIRST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NN_GATHER_BLOCKS)
 k_pair_bwd_gather(const int* __restrict__ pair_ptr, const int* __restrict__ pair_j, int N, int cap,
                   const float* __restrict__ dfb, const float* __restrict__ f_in,
                   const float* __restrict__ unit, float* __restrict__ e1_io, float* __restrict__ e2bar,
