@@ -292,6 +292,9 @@ def roofline_from_stages(ctx, stage_ms, stage_n, dev_ms, K, N, P, n_layers, work
                            launches=stage_n[name], ms_total=stage_ms[name], share=stage_ms[name] / dev_ms,
                            algorithmic_bytes_per_launch=per_launch)
     dominant = max(table, key=lambda k: table[k]['ms_total']) if table else None
+    for name in ('nbr', 'geom', 'head', 'force', 'other'):      # latency-bound / small stages: time only
+        if stage_n.get(name, 0) and stage_ms.get(name, 0.0) > 0:
+            table[name] = dict(bound='latency', launches=stage_n[name], ms_total=stage_ms[name], share=stage_ms[name] / dev_ms)
     roofline = None
     if dominant:
         t = table[dominant]

@@ -16,6 +16,13 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+// per-atom reductions (k_node_aggregate_*): atoms of one block are consecutive, so they share neighbours and pairs and
+// L1 serves the re-reads; larger blocks = more sharing per L1 working set
+#ifndef NN_AGG_THREADS
+#define NN_AGG_THREADS 256      // measured on c2 / c4: 512 threads +12..20 %, 1024 threads +6..55 % kernel time
+#endif
+constexpr int kAggThreads = NN_AGG_THREADS;
+constexpr int kAggWarps = kAggThreads / 32;
 
 __device__ __forceinline__ int dev_count(const int* n_dev, int cap) {
     int n = n_dev ? *n_dev : cap;
@@ -154,7 +161,7 @@ k_edge_message_fwd(const int* __restrict__ pair_ptr, const int* __restrict__ pai
 // ---------------------------------------------------------------------------- gather / reduce (forward)
 // a_out_i = a_i + sum_{e->i} m_p(e);  f_out_i[c] = f_i[c] + sum_{e->i} (s_e u_p[c] e1_p + e2_p * f_j[c])
 template <bool FIRST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kAggThreads)
 k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
                      const int* __restrict__ edge_pair, int N, const float* __restrict__ msg, const float* __restrict__ e1,
                      const float* __restrict__ e2, const float* __restrict__ unit, const float* __restrict__ a_in,
@@ -162,7 +169,7 @@ k_node_aggregate_fwd(const int* __restrict__ status, const int* __restrict__ row
     NN_PDL_TRIGGER();
     NN_PDL_WAIT();
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int i = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
     if (i >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;   // overflow: row_ptr is ahead of col / edge_pair
     const int r0 = row_ptr[i], r1 = row_ptr[i + 1];
     float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
@@ -379,7 +386,7 @@ __global__ void k_energy_head_seed(const float* __restrict__ h2pre, const float*
 // w[c] = dfb_i[c] - dfb_j[c];  e1bar = sum_c w[c] u[c] (overwrites e1);  ubar[c] += <w[c], e1>;
 // e2bar = sum_c dfb_i[c] * f_in_j[c] + dfb_j[c] * f_in_i[c]
 #ifndef NN_GATHER_BLOCKS
-#define NN_GATHER_BLOCKS 1      // 3 blocks (85 registers) measured: no change
+#define NN_GATHER_BLOCKS 2      // <= 128 registers; 3 blocks (85 registers): no change, 1 block (unbounded registers): +44 % time
 #endif
 template <bool FIRST>
 __global__ void __launch_bounds__(kThreads, NN_GATHER_BLOCKS)
@@ -503,14 +510,14 @@ k_pair_bwd_message(const int* __restrict__ pair_ptr, const int* __restrict__ pai
 
 // mnbar_k = sum_{e=(k,i)} t_p * mn_i ;  fbar_new_k[c] = dfb_k[c] + sum_{e=(k,i)} dfb_i[c] * e2_p
 template <bool FIRST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kAggThreads)
 k_node_aggregate_bwd(const int* __restrict__ status, const int* __restrict__ row_ptr, const int* __restrict__ col,
                      const int* __restrict__ edge_pair, int N, const float* __restrict__ t, const float* __restrict__ mn, const float* __restrict__ e2,
                      const float* __restrict__ dfb, float* __restrict__ mnbar, float* __restrict__ fbar_new) {
     NN_PDL_TRIGGER();
     NN_PDL_WAIT();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int k = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
     if (k >= N || status[NN_ST_EDGE_OVERFLOW] != 0) return;
     const int r0 = row_ptr[k], r1 = row_ptr[k + 1];
     float4 am = f4_zero(), fx = f4_zero(), fy = f4_zero(), fz = f4_zero();
@@ -736,13 +743,13 @@ int nn_node_aggregate_fwd_rows(const nn_nbr* nl, int n_rows, const float* msg, c
                                bool first_layer, cudaStream_t stream) {
     const int N = n_rows;
     if (N <= 0) return 0;
-    int grid = nn_ceil_div(N, kWarps);
+    int grid = nn_ceil_div(N, kAggWarps);
     if (first_layer) {
-        nn_launch_dep(k_node_aggregate_fwd<true>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+        nn_launch_dep(k_node_aggregate_fwd<true>, dim3(grid), dim3(kAggThreads), 0, (cudaStream_t)stream, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
                                                                                 e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
     }
     else {
-        nn_launch_dep(k_node_aggregate_fwd<false>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
+        nn_launch_dep(k_node_aggregate_fwd<false>, dim3(grid), dim3(kAggThreads), 0, (cudaStream_t)stream, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, msg,
                                                                                  e1, e2, unit, a_in, f_in, a_out, f_out); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("nn_node_aggregate_fwd");
@@ -880,12 +887,12 @@ int nn_node_aggregate_bwd_launch(const nn_nbr* nl, int n_rows, const float* t, c
                                  const float* dfb, float* mnbar, float* fbar_new, bool first, cudaStream_t s) {
     const int N = n_rows;
     if (N <= 0) return 0;
-    int grid = nn_ceil_div(N, kWarps);
+    int grid = nn_ceil_div(N, kAggWarps);
     if (first) {
-        nn_launch_dep(k_node_aggregate_bwd<true>, dim3(grid), dim3(kThreads), 0, s, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+        nn_launch_dep(k_node_aggregate_bwd<true>, dim3(grid), dim3(kAggThreads), 0, s, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
     }
     else {
-        nn_launch_dep(k_node_aggregate_bwd<false>, dim3(grid), dim3(kThreads), 0, s, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
+        nn_launch_dep(k_node_aggregate_bwd<false>, dim3(grid), dim3(kAggThreads), 0, s, nl->status, nl->row_ptr, nl->col, nl->edge_pair, N, t, mn, e2, dfb, mnbar, fbar_new); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("node_aggregate_bwd");
     return 0;

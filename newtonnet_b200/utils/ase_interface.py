@@ -72,14 +72,18 @@ class MLAseCalculator(_Calculator):
         self.properties = properties
         self.model = self.load_model(model_path)
         self._pinned = {}
+        self._resident = None        # device-resident step state of the last system shape (see _calculate_resident)
 
     # -------------------------------------------------------------- calculate (ase_interface.py:52-81)
     def calculate(self, atoms=None, properties=None, system_changes=None):
         _Calculator.calculate(self, atoms, self.properties, system_changes)
         if _is_single(atoms):
             atoms = [atoms]
-        z, pos, cell, batch = self.format_data(atoms)
         n_frames, n_atoms = len(atoms), len(atoms[0])
+        host = self._host_arrays(atoms)
+        if self._calculate_resident(host, n_frames, n_atoms):
+            return
+        z, pos, cell, batch = self._upload(host)
         pred = self.model(z, pos, cell, batch)
         for key in self.properties:
             if key in ('charges', 'bec'):
@@ -147,9 +151,12 @@ class MLAseCalculator(_Calculator):
             self._pinned[name] = buf
         return buf
 
-    def format_data(self, atoms_list):
-        """Atoms -> (z, pos, cell, batch) on the device: wrapped positions, zero rows for non-periodic
-        directions (ase_interface.py:134-138); one pinned staging copy + async H2D per tensor."""
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _host_arrays(self, atoms_list):
+        """Atoms -> numpy (z, pos, cell, batch): wrapped positions, zero rows for non-periodic directions
+        (ase_interface.py:134-138)."""
         zs, ps, cs, bs = [], [], [], []
         for b, atoms in enumerate(atoms_list):
             z = np.asarray(atoms.get_atomic_numbers(), dtype=np.int64)
@@ -160,8 +167,10 @@ class MLAseCalculator(_Calculator):
             cell[~pbc] = 0.0
             zs.append(z); ps.append(pos); cs.append(cell); bs.append(np.full(len(z), b, dtype=np.int64))
         np_dtype = {torch.float32: np.float32, torch.float64: np.float64, torch.float16: np.float16}[self.dtype]
-        host = {'z': np.concatenate(zs), 'pos': np.concatenate(ps).astype(np_dtype),
+        return {'z': np.concatenate(zs), 'pos': np.concatenate(ps).astype(np_dtype),
                 'cell': np.stack(cs).astype(np_dtype), 'batch': np.concatenate(bs)}
+
+    def _upload(self, host):
         out = []
         for name in ('z', 'pos', 'cell', 'batch'):
             src = torch.from_numpy(host[name])
@@ -169,3 +178,85 @@ class MLAseCalculator(_Calculator):
             stage.copy_(src)
             out.append(stage.to(self.device, non_blocking=True))
         return tuple(out)
+
+    def format_data(self, atoms_list):
+        """Atoms -> (z, pos, cell, batch) on the device; one pinned staging copy + async H2D per tensor."""
+        return self._upload(self._host_arrays(atoms_list))
+
+    # -------------------------------------------------------------- device-resident MD-step path (SURVEY 8f rank 1)
+    def _calculate_resident(self, host, n_frames, n_atoms):
+        """Steady-state path of an MD driver (reference: ase_interface.py:52-81 re-uploads z / cell / batch, launches the
+        whole model from Python and reads every result back with its own synchronisation, every step).  From the second
+        call with the same system shape on, atomic numbers, cell and batch stay resident on the device (re-sent only when
+        they change), the positions go from a pinned buffer straight into the static input of ONE CUDA graph (neighbour
+        rebuild + evaluation), and status, energy, forces and stress come back as asynchronous copies into pinned memory
+        behind a single stream synchronisation.  Returns False when the general path has to run."""
+        from newtonnet_b200 import _lib as L
+        from newtonnet_b200.engine import GraphedStep, get_engine
+        props = self.properties
+        if self.dtype != torch.float32 or any(k not in ('energy', 'free_energy', 'forces', 'stress') for k in props):
+            return False
+        mp = list(self.model.output_properties)
+        if any(k not in ('energy', 'gradient_force', 'stress', 'virial') for k in mp) or 'energy' not in mp:
+            return False
+        if any(getattr(layer, 'create_graph', False) for layer in self.model.output_layers) or self.model.training:
+            return False
+        engine = get_engine(self.device)
+        if not engine.use_cuda_graphs:
+            return False
+        want_virial = 'stress' in mp or 'virial' in mp
+        want_forces = 'gradient_force' in mp or want_virial
+        N, B = host['pos'].shape[0], host['cell'].shape[0]
+        key = (N, B, want_forces, want_virial, tuple(props))
+        st = self._resident
+        if st is None or st['key'] != key:
+            if st is not None and st.get('pending_key') == key and engine._nl is not None and engine._nl.n_atoms == N:
+                # second call with this shape: capacities are known from the general path's call -> capture the step
+                pack = self.model._weight_pack(self.device)
+                z, pos, cell, batch = self._upload(host)
+                step = GraphedStep(engine, pack, z, pos, cell, batch, want_forces, want_virial, False, engine._nl.cap_edges)
+                pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+                self._resident = st = {
+                    'key': key, 'step': step, 'pack': pack, 'sig': self._param_signature(),
+                    'host': {k: host[k].copy() for k in ('z', 'cell', 'batch')},
+                    'pos_pin': pin((N, 3), torch.float32), 'status_pin': pin((L.NN_STATUS_WORDS,), torch.int32),
+                    'e_pin': pin((B,), torch.float32), 'f_pin': pin((N, 3), torch.float32) if want_forces else None,
+                    's_pin': pin((B, 3, 3), torch.float32) if want_virial else None}
+            else:
+                self._resident = {'key': None, 'pending_key': key}
+                return False
+        step = st['step']
+        if st['sig'] != self._param_signature():                          # parameters changed: recapture via the general path
+            self._resident = None
+            return False
+        for name, dst in (('z', step.z), ('cell', step.cell), ('batch', step.batch)):
+            if not np.array_equal(host[name], st['host'][name]):
+                dst.copy_(torch.from_numpy(host[name]).to(dst.dtype).reshape(dst.shape))
+                st['host'][name] = host[name].copy()
+        st['pos_pin'].copy_(torch.from_numpy(host['pos']))
+        step.pos.copy_(st['pos_pin'], non_blocking=True)
+        step.nl.n_edges = None
+        step.nl.generation += 1
+        step.graph.replay()
+        st['status_pin'].copy_(step.nl.status, non_blocking=True)
+        st['e_pin'].copy_(step.out['energy'], non_blocking=True)
+        if want_forces:
+            st['f_pin'].copy_(step.out['forces'], non_blocking=True)
+        if want_virial:
+            st['s_pin'].copy_(step.out['stress'], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()             # the one synchronisation of the step
+        status = st['status_pin'].tolist()
+        if status[L.ST_EDGE_OVERFLOW] or status[L.ST_ROW_OVERFLOW] or status[L.ST_BATCH_UNSORTED] or status[L.ST_SINGULAR_CELL]:
+            self._resident = None            # capacity outgrown or bad input: the general path regrows / raises
+            return False
+        energy = st['e_pin'].numpy().copy()
+        if 'energy' in props:
+            self.results['energy'] = energy.squeeze()
+        if 'free_energy' in props:
+            self.results['free_energy'] = energy.squeeze()
+        if 'forces' in props:
+            self.results['forces'] = st['f_pin'].numpy().copy().reshape(n_frames, n_atoms, 3).squeeze()
+        if 'stress' in props:
+            stress = st['s_pin'].numpy().copy()
+            self.results['stress'] = stress[:, [0, 1, 2, 1, 0, 0], [0, 1, 2, 2, 2, 1]].squeeze()   # Voigt
+        return True

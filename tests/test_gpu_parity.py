@@ -652,3 +652,39 @@ def test_general_cells_grid_search_matches_dense_reference_search(kind):
     assert ref_ei.shape[1] > 1000
     assert np.array_equal(ei.cpu().numpy(), ref_ei.numpy())
     assert np.abs(disp.cpu().numpy() - ref_d.numpy()).max() < 2e-5
+
+
+def test_ase_calculator_resident_md_path(tmp_path):
+    """The calculator's steady-state path (device-resident z / cell / batch, one CUDA graph, one synchronisation): the same
+    numbers as the general path, step after step; it follows changes of the cell, of the atomic numbers and of the model
+    parameters, and it survives a capacity overflow (denser positions)."""
+    from newtonnet_b200.compat import model_from_state_dict
+    from newtonnet_b200.utils.ase_interface import MLAseCalculator
+    d, ws = load_case('water375')
+    model = model_from_state_dict({k: torch.tensor(v) for k, v in ws.items()})
+    calc = MLAseCalculator(model, properties=['energy', 'forces', 'stress'], device='cuda:0')
+    ref = MLAseCalculator(model_from_state_dict({k: torch.tensor(v) for k, v in ws.items()}), properties=['energy', 'forces', 'stress'],
+                          device='cuda:0')
+    import newtonnet_b200.engine as E
+    rng = np.random.default_rng(0)
+    pos, cell, z = d['pos'].astype(np.float64), d['cell'][0].astype(np.float64), d['z'].copy()
+
+    def both(z_, pos_, cell_):
+        calc.calculate(FakeAtoms(z_, pos_, cell_, True))
+        ref._resident = None                                   # general path every time
+        ref.calculate(FakeAtoms(z_, pos_, cell_, True))
+        for k in ('energy', 'forces', 'stress'):
+            assert np.array_equal(np.asarray(calc.results[k]), np.asarray(ref.results[k])), k
+
+    for step in range(5):
+        both(z, pos + rng.normal(0, 0.02, pos.shape), cell)
+    assert calc._resident is not None and calc._resident['key'] is not None     # the resident path is active
+    both(z, pos * 1.01, cell * 1.01)                           # cell change
+    z2 = z.copy(); z2[::7] = 6
+    both(z2, pos, cell)                                        # other atomic numbers
+    both(z, pos * 0.85, cell * 0.85)                           # much denser: capacity overflow -> general path regrows
+    both(z, pos * 0.85 + rng.normal(0, 0.01, pos.shape), cell * 0.85)
+    with torch.no_grad():
+        for m in (calc.model, ref.model):
+            m.scalers[0].shift.weight.add_(0.5)
+    both(z, pos, cell)                                         # parameter update is picked up

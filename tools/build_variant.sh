@@ -7,7 +7,7 @@ name="$1"; file="$2"; flags="$3"
 src="$root/newtonnet_b200/csrc"
 mkdir -p "$root/variants"
 objs=()
-for f in nbr gemm_simt gemm_tc gemm_ts gemm_chain message_tc pair_ops eval train_ops p2p md_ops; do
+for f in nbr gemm_simt gemm_tc gemm_ts gemm_chain gemm_tn_tc message_tc pair_ops eval train_ops p2p md_ops; do
   if [ "$f" == "$file" ]; then
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
       --expt-relaxed-constexpr -DNN_BUILD $flags -c "$src/$f.cu" -o "$root/variants/$name.$f.o"

@@ -57,8 +57,11 @@ def main():
         print(f'{name[:58]:58s} {t[0]:4d} {t[1]:10.1f} {100 * t[1] / total_us:5.1f}% {t[2] / 1e9:8.3f} {t[3] / 1e9:8.3f} '
               f'{(t[2] + t[3]) / max(t[1], 1e-9) * 1e-3:7.0f}')
     pair = [d for d in step if ('k_gemm128_chain' in d['name'] or 'k_gemm128_ts' in d['name']) and int(d['grid'].strip('()').split(',')[0]) >= 140]
-    # pair-level launches run on the full grid (one CTA per SM); node-level ones on small inputs may too - keep those with > 1 GB
-    pair = [d for d in pair if d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) > 0.2e9]
+    # pair-level launches run on the full grid (one CTA per SM); node-level ones on 3N rows do too - a pair-level launch moves
+    # at least 1 KB per pair, i.e. it is within a factor ~3 of the largest launch, node-level ones are >= 9x smaller
+    byt = lambda d: d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0)
+    top = max((byt(d) for d in pair), default=0.0)
+    pair = [d for d in pair if byt(d) > 0.3 * top]
     if pair and '--write' in sys.argv:
         commit = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], cwd=ROOT, capture_output=True, text=True).stdout.strip()
         out = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
