@@ -51,6 +51,14 @@ static bool chain_enabled() {          // two-CTA chained GEMM pairs (gemm_chain
     return v == 1;
 }
 
+// node-level MLPs (no device row count) take the chained kernel when they are small enough to be launch-latency-bound:
+// one launch instead of two (measured: see DESIGN.md); 0 = never.  Large node-level inputs stay on two launches.
+static int chain_small_m() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NN_CHAIN_SMALL_M"); v = e ? atoi(e) : 20000; }
+    return v;
+}
+
 bool nn_pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("NN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -196,7 +204,7 @@ struct Gemm {
     void mlp_fwd(const float* X, const nn_mat& M1, const float* b1, float* mid, const nn_mat& M2, const float* b2, float* Y,
                  int m, int pro_act, const int* m_dev = nullptr) {
         if (rc) return;
-        if (g_backend == 2 && chain_enabled() && m_dev && M1.wt_img && M2.wt_img) {     // pair-level only (gemm_chain.cu)
+        if (g_backend == 2 && chain_enabled() && (m_dev || m <= chain_small_m()) && M1.wt_img && M2.wt_img) {     // gemm_chain.cu
             ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
             nn_gemm_chain_args a{};
             a.X = X; a.B1_img = M1.wt_img; a.B2_img = M2.wt_img; a.bias1 = b1; a.bias2 = b2; a.aux_out = mid; a.Y = Y;
@@ -211,7 +219,7 @@ struct Gemm {
     void mlp_bwd(const float* G, const nn_mat& M2, const float* dact, float* tmp, const nn_mat& M1, float* Y, int m,
                  bool accumulate, const int* m_dev = nullptr) {
         if (rc) return;
-        if (g_backend == 2 && chain_enabled() && m_dev && accumulate && M1.w_img && M2.w_img) {
+        if (g_backend == 2 && chain_enabled() && ((m_dev && accumulate) || (!m_dev && m <= chain_small_m())) && M1.w_img && M2.w_img) {
             ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
             nn_gemm_chain_args a{};
             a.X = G; a.B1_img = M2.w_img; a.B2_img = M1.w_img; a.aux1 = dact; a.aux2 = accumulate ? Y : nullptr; a.Y = Y;
