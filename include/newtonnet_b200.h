@@ -191,6 +191,11 @@ typedef struct {
     const int32_t* m_dev; int32_t m_dev_mul;   /* rows = m_dev[0] * m_dev_mul when m_dev != NULL */
     int32_t m;
     int32_t mid, out;
+    /* optional SECOND chain over the same X (NULL = none): Y_b = out( mid(X . B1_img_b) . B2_img_b ), aux_out_b its mid
+     * output; same mid / out steps, no biases.  The two chains run in one launch, odd / even clusters walking the tiles
+     * in lockstep, so X is fetched from HBM once (the second read is an L2 hit): equiv_message1 and equiv_message2 of one
+     * layer share their input (models/newtonnet.py:218,222). */
+    const float* B1_img_b; const float* B2_img_b; float* aux_out_b; float* Y_b;
 } nn_gemm_chain_args;
 NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream);
 /* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo

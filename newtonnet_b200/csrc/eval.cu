@@ -215,6 +215,21 @@ struct Gemm {
         fwd(X, M1, mid, m, NN_PRO_NONE, NN_EPI_BIAS, b1, nullptr, nullptr, nullptr, m_dev);
         fwd(mid, M2, Y, m, pro_act, NN_EPI_BIAS, b2, nullptr, nullptr, nullptr, m_dev);
     }
+    // two forward MLPs over the same input in one dual launch (equiv_message1 / equiv_message2: X is read from HBM once)
+    bool mlp_fwd_dual(const float* X, const nn_mat& A1, float* midA, const nn_mat& A2, float* YA, const nn_mat& B1, float* midB,
+                      const nn_mat& B2, float* YB, int m, const int* m_dev) {
+        if (rc) return true;
+        static int dual_on = -1;
+        if (dual_on < 0) { const char* e = getenv("NN_CHAIN_DUAL"); dual_on = (e && e[0] == '1') ? 1 : 0; }
+        if (!(g_backend == 2 && chain_enabled() && dual_on && m_dev && A1.wt_img && A2.wt_img && B1.wt_img && B2.wt_img)) return false;
+        ProfScope ps(NN_STAGE_PAIR_GEMM, s);
+        nn_gemm_chain_args a{};
+        a.X = X; a.B1_img = A1.wt_img; a.B2_img = A2.wt_img; a.aux_out = midA; a.Y = YA;
+        a.B1_img_b = B1.wt_img; a.B2_img_b = B2.wt_img; a.aux_out_b = midB; a.Y_b = YB;
+        a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_SILU_SAVE; a.out = NN_OUT_BIAS;
+        rc = nn_gemm128_chain(&a, s);
+        return true;
+    }
     // Y (+)= ((G @ M2) * dact) @ M1 (reverse MLP); `tmp` receives the intermediate on the two-launch path only
     void mlp_bwd(const float* G, const nn_mat& M2, const float* dact, float* tmp, const nn_mat& M1, float* Y, int m,
                  bool accumulate, const int* m_dev = nullptr) {
@@ -323,9 +338,10 @@ int run_phase(EvalCtx& c, int phase, int l) {
             if (g_backend >= 1 && lw.We_img) NN_TRY(nn_message_fwd_tc(nl, w.rbf, b.mn, lw.We_img, b.msg, s));
             else NN_TRY(nn_edge_message_fwd(nl, w.rbf, b.mn, lw.Wet, b.msg, s));
         }
-        g.mlp_fwd(b.msg, lw.U1, nullptr, b.q1, lw.U2, nullptr, b.e1, P, c.PRO_ACT, np_dev);
-        if (!first) {   // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing
-            g.mlp_fwd(b.msg, lw.V1, nullptr, b.q2, lw.V2, nullptr, b.e2, P, c.PRO_ACT, np_dev);
+        // layer 0: force_node == 0, so equiv_message2 contributes exactly nothing; other layers: both MLPs in one dual launch
+        if (first || !g.mlp_fwd_dual(b.msg, lw.U1, b.q1, lw.U2, b.e1, lw.V1, b.q2, lw.V2, b.e2, P, np_dev)) {
+            g.mlp_fwd(b.msg, lw.U1, nullptr, b.q1, lw.U2, nullptr, b.e1, P, c.PRO_ACT, np_dev);
+            if (!first) g.mlp_fwd(b.msg, lw.V1, nullptr, b.q2, lw.V2, nullptr, b.e2, P, c.PRO_ACT, np_dev);
         }
         NN_TRY(g.rc);
         { ProfScope ps(NN_STAGE_AGGREGATE, s); NN_TRY(nn_node_aggregate_fwd_rows(nl, No, b.msg, b.e1, b.e2, w.unit, a_cur, f_in, a_nxt, b.f_out, first, s)); }

@@ -180,7 +180,16 @@ __device__ __forceinline__ void epilogue_role(const nn_gemm_chain_args& a, const
 }
 
 template <int MID, int OUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm128_chain(nn_gemm_chain_args a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm128_chain(nn_gemm_chain_args a_in) {
+    // dual launch (Y_b != NULL): even clusters run chain A, odd clusters chain B over the same X tiles
+    nn_gemm_chain_args a = a_in;
+    const bool dual = a_in.Y_b != nullptr;
+    {
+        uint32_t c; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(c));
+        if (dual && (c & 1u)) {
+            a.B1_img = a_in.B1_img_b; a.B2_img = a_in.B2_img_b; a.aux_out = a_in.aux_out_b; a.Y = a_in.Y_b;
+        }
+    }
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = base;                                             // this rank's weight image [hi|lo][kb][16 KB]
@@ -199,7 +208,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
-    const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+    const int cid = dual ? (int)(cluster_id_x() >> 1) : (int)cluster_id_x();
+    const int ncl = dual ? (int)(n_clusters_x() >> 1) : (int)n_clusters_x();
 
     pdl_launch_dependents();
     if (warp == MMA_WARP) {
@@ -363,7 +373,11 @@ int launch(const nn_gemm_chain_args& a, cudaStream_t s) {
         g_pairs = sms > 1 ? sms / 2 : 74;
     }
     const int tiles = nn_ceil_div(a.m, TM);
-    const int clusters = tiles < g_pairs ? tiles : g_pairs;
+    int clusters = tiles < g_pairs ? tiles : g_pairs;
+    if (a.Y_b) {                                   // dual: an even number of clusters, half per chain
+        clusters = 2 * tiles < g_pairs ? 2 * tiles : (g_pairs & ~1);
+        if (clusters < 2) clusters = 2;
+    }
     NN_LAUNCHED(1);
     return launch_pdl(k_gemm128_chain<MID, OUT>, 2 * clusters, THREADS, SMEM_BYTES, s, a);
 }
@@ -377,6 +391,8 @@ extern "C" NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream
     NN_REQUIRE(a->mid != MID_SILU_SAVE || a->aux_out, "mid = SILU_SAVE needs aux_out");
     NN_REQUIRE(a->mid != MID_MUL || a->aux1, "mid = MUL needs aux1");
     NN_REQUIRE(a->out != OUT_ADD || a->aux2, "out = ADD needs aux2");
+    NN_REQUIRE(!a->Y_b || (a->B1_img_b && a->B2_img_b && (a->mid != MID_SILU_SAVE || a->aux_out_b) && a->out == OUT_BIAS && !a->bias1 && !a->bias2),
+               "dual chain: needs B1_img_b, B2_img_b, aux_out_b, out = BIAS and no biases");
     if (a->m <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;

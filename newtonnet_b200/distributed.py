@@ -170,10 +170,14 @@ class PeerArena:
         self.plan, self.group, self.device = plan, group, torch.device(device)
         self.lib = L.load()
         self.rank, self.world = plan.rank, plan.world
+        self.n_atoms_total = int(n_atoms_total)
         if not 2 <= self.world <= L.DD_MAX_RANKS:
             raise ValueError(f'peer-memory transport supports 2..{L.DD_MAX_RANKS} ranks')
         al = lambda n: (int(n) + 255) // 256 * 256
-        landing = al(max(plan.n_ghost, 1) * L.DD_MAX_WIDTH * 4)
+        # room for the ghost count to grow: a later plan of the same box (atoms drift, the ghost shell is re-cut) reuses
+        # the arena and its IPC mappings (`rebind`) instead of paying cudaMalloc + handle exchange + mapping again
+        self.ghost_cap = int(plan.n_ghost * 1.25) + 1024
+        landing = al(self.ghost_cap * L.DD_MAX_WIDTH * 4)
         off, cur = {}, 0
         for ch in range(L.DD_CHANNELS):
             for par in range(2):
@@ -212,12 +216,7 @@ class PeerArena:
                 c.landing[ch][par] = self.base + off['landing', ch, par]
         c.forces_full = self.base + off['forces']
         c.partials = self.base + off['partials']
-        begin = 0
         for s in range(self.world):
-            c.send_begin[s] = begin
-            begin += plan.send_counts[s]
-            c.send_end[s] = begin
-            c.row_offset[s] = plan.send_row_offset[s]
             if s == self.rank:
                 continue
             o = gathered[s][1]
@@ -227,11 +226,35 @@ class PeerArena:
                     c.peer_landing[ch][par][s] = self.opened[s] + o['landing', ch, par]
             c.peer_forces_full[s] = self.opened[s] + o['forces']
             c.peer_partials[s] = self.opened[s] + o['partials']
-        c.send_idx = self.send_index.data_ptr()
         c.step, c.done, c.status = self.step.data_ptr(), self.done.data_ptr(), self.status.data_ptr()
         self.comm = c
-        self.bytes_per_row_exchange = lambda width: 4 * width * int(plan.send_index.shape[0])
+        self._bind_plan(plan)
         dist.barrier(group=group)
+
+    def _bind_plan(self, plan):
+        c = self.comm
+        self.plan = plan
+        self.send_index = torch.from_numpy(plan.send_index).to(self.device)
+        c.n_owned, c.n_ghost = plan.n_owned, plan.n_ghost
+        begin = 0
+        for s in range(self.world):
+            c.send_begin[s] = begin
+            begin += plan.send_counts[s]
+            c.send_end[s] = begin
+            c.row_offset[s] = plan.send_row_offset[s]
+        c.send_idx = self.send_index.data_ptr()
+
+    def fits(self, plan, n_atoms_total):
+        return plan.n_ghost <= self.ghost_cap and int(n_atoms_total) == self.n_atoms_total and plan.world == self.world
+
+    def rebind(self, plan):
+        """Adopt a new brick / ghost plan of the same box (same ranks, same arena, same peer mappings).  Every rank does this
+        after the same step (the stale flag is OR-ed over ranks), and a rank can only have finished that step after all
+        its peers consumed what it sent, so nobody still reads landing data of the old plan.  The sticky status words are
+        cleared; the step counter and the flag epochs keep running."""
+        torch.cuda.synchronize(self.device)
+        self.status.zero_()
+        self._bind_plan(plan)
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -247,7 +270,9 @@ class _PeerStep:
     """One decomposed evaluation over static buffers: launched eagerly the first time, then captured and replayed
     as ONE CUDA graph (two streams: halo exchanges off the critical path run on the side stream)."""
 
-    def __init__(self, dd, z, pos, cell3, want_virial):
+    def __init__(self, dd, z, pos, cell3, want_virial, reuse=None):
+        """reuse: the step object of the previous plan of the same box - its arena (peer mappings) and its neighbour-list
+        capacities are taken over when they fit, and the first call is captured right away (every kernel has run before)."""
         from newtonnet_b200.engine import NeighborList, get_engine
         self.dd = dd
         dev = pos.device
@@ -265,7 +290,19 @@ class _PeerStep:
         self.plan = plan
         nL = self.pack.n_layers
         self.strides = (2 * nL + 1, max(2 * nL - 1, 1))
-        self.arena = PeerArena(plan, N, dev, dd.group, self.strides)
+        fits = reuse is not None and reuse.arena is not None and reuse.arena.fits(plan, N) and reuse.strides == self.strides
+        if dd.world > 1:      # the same decision on every rank (a collective constructor must not be entered by some ranks only)
+            flag = torch.tensor([0.0 if fits else 1.0], device=dev)
+            dist.all_reduce(flag, group=dd.group)
+            fits = bool(flag.item() == 0)
+        if fits:
+            self.arena = reuse.arena
+            reuse.arena = None                   # ownership moves here
+            self.arena.rebind(plan)
+        else:
+            if reuse is not None:
+                reuse.close()
+            self.arena = PeerArena(plan, N, dev, dd.group, self.strides)
         f32 = dict(dtype=torch.float32, device=dev)
         self.n_local, self.n_owned = len(plan.local_to_global), plan.n_owned
         self.l2g = torch.from_numpy(plan.local_to_global.astype(np.int32)).to(dev)
@@ -287,9 +324,17 @@ class _PeerStep:
         self.side = torch.cuda.Stream(device=dev)
         self.graph = None
         self.calls = 0
+        self.stale = False
         self._NeighborList = NeighborList
         self.nl = None
-        self._size_neighbor_list()
+        if fits and reuse.nl is not None:
+            # capacities of the previous plan, scaled by the change of the owned count, plus headroom (an overflow is caught by
+            # the status words like any other)
+            g = max(1.0, self.n_owned / max(reuse.n_owned, 1)) * 1.02
+            self._size_neighbor_list(caps=(int(reuse.nl.cap_edges * g) + 64, int(reuse.nl.cap_pairs * g) + 64))
+            self.calls = 1               # no eager first step: capture immediately
+        else:
+            self._size_neighbor_list()
 
     # ---- capacities
     def _new_list(self, cap_edges, cap_pairs):
@@ -297,10 +342,15 @@ class _PeerStep:
         nl.struct.n_owned = self.n_owned
         return nl
 
-    def _size_neighbor_list(self, needed=None):
+    def _size_neighbor_list(self, needed=None, caps=None):
         """Probe: count (-> directed edges of the owned rows), then a trial fill with room for one pair per edge (ghost rows
-        are empty, so an owned-ghost pair has a single directed edge and P lies between E / 2 and E) -> final capacities."""
+        are empty, so an owned-ghost pair has a single directed edge and P lies between E / 2 and E) -> final capacities.
+        caps = (cap_edges, cap_pairs): take these instead of probing."""
         s = torch.cuda.current_stream().cuda_stream
+        if caps is not None:
+            self.nl = self._new_list(caps[0] + caps[0] % 2, caps[1])
+            self._bind_eval()
+            return
         probe = self._new_list(0, 0)
         L.check(self.lib.nn_nbr_count(C.byref(probe.struct), self.pack.cutoff, s), 'nn_nbr_count')
         n_edges = max(probe.check()[L.ST_N_EDGES], int(needed or 0))
@@ -311,6 +361,9 @@ class _PeerStep:
         cap = int(st[L.ST_N_EDGES] * 1.08) + 64
         self.nl = self._new_list(cap + cap % 2, int(st[L.ST_N_PAIRS] * 1.08) + 64)
         del probe
+        self._bind_eval()
+
+    def _bind_eval(self):
         nbytes = self.lib.nn_eval_workspace_bytes(self.n_local, 1, self.nl.cap_pairs, self.pack.n_layers, 1)
         self.ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         a = L.EvalArgs()
@@ -413,7 +466,9 @@ class _PeerStep:
 
     def close(self):
         self.graph = None
-        self.arena.close()
+        if self.arena is not None:
+            self.arena.close()
+            self.arena = None
 
 
 class DomainDecomposition:
@@ -467,10 +522,11 @@ class DomainDecomposition:
         N = pos.shape[0]
         for attempt in range(4):
             p = self._peer
-            if p is None or p.N != N or p.want_virial != bool(want_virial):
-                if p is not None:
+            if p is None or p.N != N or p.want_virial != bool(want_virial) or p.stale:
+                same_box = p is not None and p.N == N and p.want_virial == bool(want_virial)
+                if p is not None and not same_box:
                     p.close()
-                p = self._peer = _PeerStep(self, z, pos, cell3, want_virial)
+                p = self._peer = _PeerStep(self, z, pos, cell3, want_virial, reuse=p if same_box else None)
                 self.plan = p.plan
                 self.n_plans += 1
             p.run(z, pos, cell3)
@@ -483,8 +539,7 @@ class DomainDecomposition:
                 p.nl.check()
                 raise RuntimeError('neighbour list failure on a peer rank (degree overflow / singular cell)')
             if st[L.DD_ST_STALE]:                        # same decision on every rank: the flags were OR-ed by nn_dd_finish
-                p.close()
-                self._peer = None
+                p.stale = True                           # re-cut the bricks for the new positions, keep arena and capacities
                 continue
             if st[L.DD_ST_OVERFLOW]:
                 need = p.nl.status.cpu().tolist()

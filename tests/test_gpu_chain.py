@@ -70,3 +70,38 @@ def test_chain_argument_errors():
     a = L.GemmChainArgs()
     assert lib.nn_gemm128_chain(C.byref(a), None) != 0
     assert b'null' in lib.nn_last_error()
+
+
+@pytest.mark.parametrize('M', [1, 128, 129, 4099, 74 * 128 * 3 + 77, 148 * 128 * 5 + 1])
+def test_dual_chain_matches_two_single_chains(M):
+    """Two forward MLPs over the same input in ONE launch (odd / even clusters, X fetched from HBM once): bit-identical to
+    two chained launches; device-side row count honoured."""
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    lib.nn_set_gemm_backend(2)
+    g = torch.Generator(device='cpu').manual_seed(1000 + M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev())
+    X = r(M, 128)
+    A1, A2, B1, B2 = (r(128, 128) / 11.3 for _ in range(4))
+    s = torch.cuda.current_stream().cuda_stream
+    imgs = []
+    for B in (A1, A2, B1, B2):
+        img = torch.empty(L.NN_B_IMAGE_FLOATS, device=X.device)
+        L.check(lib.nn_gemm128_prepare_b(B.data_ptr(), img.data_ptr(), s), 'prepare_b')
+        imgs.append(img)
+    midA, midB = torch.empty_like(X), torch.empty_like(X)
+    wantA = _chain(lib, X, A1, A2, 0, 0, aux_out=midA)
+    wantB = _chain(lib, X, B1, B2, 0, 0, aux_out=midB)
+    cnt = torch.tensor([max(M - 50, 1)], dtype=torch.int32, device=dev())
+    for m_dev in (None, cnt):
+        n = M if m_dev is None else int(cnt.item())
+        YA, YB, mA, mB = (torch.full_like(X, 3.0) for _ in range(4))
+        a = L.GemmChainArgs()
+        a.X, a.B1_img, a.B2_img, a.Y, a.aux_out = X.data_ptr(), imgs[0].data_ptr(), imgs[1].data_ptr(), YA.data_ptr(), mA.data_ptr()
+        a.B1_img_b, a.B2_img_b, a.Y_b, a.aux_out_b = imgs[2].data_ptr(), imgs[3].data_ptr(), YB.data_ptr(), mB.data_ptr()
+        a.m_dev, a.m_dev_mul, a.m, a.mid, a.out = L.ptr(m_dev), 1, M, 0, 0
+        L.check(lib.nn_gemm128_chain(C.byref(a), s), 'nn_gemm128_chain(dual)')
+        torch.cuda.synchronize()
+        assert torch.equal(YA[:n], wantA[:n]) and torch.equal(YB[:n], wantB[:n])
+        assert torch.equal(mA[:n], midA[:n]) and torch.equal(mB[:n], midB[:n])
+        assert bool((YA[n:] == 3.0).all()) and bool((mB[n:] == 3.0).all())
