@@ -372,6 +372,23 @@ NN_API int nn_segment_sum(const float* src, const int32_t* perm, const int32_t* 
 NN_API size_t nn_gemm128_tn_workspace_bytes(int32_t m);
 NN_API int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream);
 
+/* Fused row products of the training path: the element-wise glue of InteractionNet.forward (models/newtonnet.py:211,
+ * 219-226,231) as kernels that are closed under differentiation (each gradient is a combination of the others), so
+ * autograd composes forward / backward / double backward from them.  Rows of F = 128 floats.
+ *   nn_ew_mul3: out = a * b * c (n_floats elements).
+ *   nn_ew_rows(mode): p [n,F], q3 [n,3,F], u [n,3]:
+ *     0 outer      out[n,3,F] = p[e,:] * u[e,c]            1 contract_c  out[n,F] = sum_c q3[e,c,:] * u[e,c]
+ *     2 row_dot    out[n,3]   = <q3[e,c,:], p[e,:]>        3 mul_b       out[n,3,F] = p[e,:] * q3[e,c,:]
+ *     4 sum_mul_c  out[n,F]   = sum_c q3[e,c,:] * p3[e,c,:]   (the second [n,3,F] operand is passed as p) */
+NN_API int nn_ew_mul3(const float* a, const float* b, const float* c, float* out, int64_t n_floats, void* stream);
+NN_API int nn_ew_rows(int32_t mode, const float* p, const float* q3, const float* u, float* out, int32_t n_rows, void* stream);
+/* SiLU with its first two derivatives (layers/activations.py:13 nn.SiLU under autograd twice): mode 0 out = silu(x);
+ * mode 1 out = a * silu'(x); mode 2 out = a * b * silu''(x). */
+/* Radial basis R_n(x) = env(x) sin(f_n x) / x (representations.py:166-169,233) with its x-derivatives of order k = 0..2:
+ * op 0 (scale): out[e,n] = (a ? a[e] : 1) * R^k_n(x[e])  ([n_rows, 20]);  op 1 (dot): out[e] = sum_n a[e,n] R^k_n(x[e]). */
+NN_API int nn_ew_rbf(int32_t op, int32_t k, const float* a, const float* x, const float* freq, float* out, int32_t n_rows, void* stream);
+NN_API int nn_ew_silu(int32_t mode, const float* x, const float* a, const float* b, float* out, int64_t n_floats, void* stream);
+
 /* ---- reverse-sweep operators as standalone entry points; nn_eval composes exactly these.
  * They replace the autograd replay of DerivativeProperty._save_grad (models/output.py:66-73) piece by piece. */
 /* Y = silu(X M1^T + b1) M2^T + b2; `mid` receives the pre-activation, or silu'(pre-activation) when save_dact != 0 (what

@@ -113,6 +113,10 @@ SYMBOLS = {
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    'nn_ew_mul3': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
+    'nn_ew_rows': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
+    'nn_ew_silu': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int64, _fp]),
+    'nn_ew_rbf': (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_gemm128_chain': (C.c_int, [C.POINTER(GemmChainArgs), _fp]),
     'nn_mlp_fwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, _fp, C.c_int32, _fp, C.c_int32, _fp]),
     'nn_mlp_bwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, C.c_int32, _fp, C.c_int32, _fp]),

@@ -220,7 +220,7 @@ struct Gemm {
                       const nn_mat& B2, float* YB, int m, const int* m_dev) {
         if (rc) return true;
         static int dual_on = -1;
-        if (dual_on < 0) { const char* e = getenv("NN_CHAIN_DUAL"); dual_on = (e && e[0] == '1') ? 1 : 0; }
+        if (dual_on < 0) { const char* e = getenv("NN_CHAIN_DUAL"); dual_on = (e && e[0] == '0') ? 0 : 1; }
         if (!(g_backend == 2 && chain_enabled() && dual_on && m_dev && A1.wt_img && A2.wt_img && B1.wt_img && B2.wt_img)) return false;
         ProfScope ps(NN_STAGE_PAIR_GEMM, s);
         nn_gemm_chain_args a{};

@@ -133,3 +133,200 @@ extern "C" int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* o
     NN_CHECK_LAUNCH("nn_gemm128_tn");
     return 0;
 }
+
+// ---------------------------------------------------------------------------- fused row products of the training path
+// The element-wise glue of InteractionNet.forward (reference models/newtonnet.py:211,219-226,231) as six bilinear /
+// trilinear row kernels that are CLOSED under differentiation - the gradient of each is a combination of the others - so
+// autograd composes forward, backward and double backward from them without falling back to broadcasting ATen kernels
+// (which were ~700 of the ~1400 launches of a config-5 training step).  Rows of F = 128 floats, one warp per row,
+// float4 per lane; `x3` tensors are [n, 3, F], `u` tensors [n, 3].
+//   mul3      out = a * b * c                                   d/da = mul3(g, b, c) ...
+//   outer     out[e,c,:] = x[e,:] * u[e,c]                      d/dx = contract_c(g, u),  d/du = row_dot(g, x)
+//   contract  out[e,:]   = sum_c x3[e,c,:] * u[e,c]             d/dx3 = outer(g, u),      d/du = row_dot(x3, g)
+//   row_dot   out[e,c]   = <x3[e,c,:], x[e,:]>                  d/dx3 = outer(x, g),      d/dx = contract_c(x3, g)
+//   mul_b     out[e,c,:] = x[e,:] * y3[e,c,:]                   d/dx = sum_mul_c(g, y3),  d/dy3 = mul_b(x, g)
+//   sum_mul_c out[e,:]   = sum_c x3[e,c,:] * y3[e,c,:]          d/dx3 = mul_b(g, y3),     d/dy3 = mul_b(g, x3)
+namespace {
+
+__global__ void k_ew_mul3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                          float* __restrict__ out, long long n4) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
+        st4(out + 4 * t, f4_mul(ld4(a + 4 * t), f4_mul(ld4(b + 4 * t), ld4(c + 4 * t))));
+}
+
+// mode 0 outer, 1 contract_c, 2 row_dot, 3 mul_b, 4 sum_mul_c; p = [n,F] operand, q3 = [n,3,F] operand, u = [n,3] operand
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_ew_rows(const float* __restrict__ p, const float* __restrict__ q3, const float* __restrict__ u, float* __restrict__ out, int n) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= n) return;
+    const size_t r = (size_t)e * kF + 4 * lane, r3 = (size_t)e * 3 * kF + 4 * lane;
+    if (MODE == 0) {            // outer(p, u)
+        const float4 x = ld4(p + r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) st4(out + r3 + c * kF, f4_fma(u[3 * e + c], x, f4_zero()));
+    } else if (MODE == 1) {     // contract_c(q3, u)
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc = f4_fma(u[3 * e + c], ld4(q3 + r3 + c * kF), acc);
+        st4(out + r, acc);
+    } else if (MODE == 2) {     // row_dot(q3, p)
+        const float4 x = ld4(p + r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float s = warp_sum(f4_dot(ld4(q3 + r3 + c * kF), x));
+            if (lane == 0) out[3 * e + c] = s;
+        }
+    } else if (MODE == 3) {     // mul_b(p, q3)
+        const float4 x = ld4(p + r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) st4(out + r3 + c * kF, f4_mul(x, ld4(q3 + r3 + c * kF)));
+    } else {                    // sum_mul_c(q3, second [n,3,F] operand passed in p)
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc = f4_fma(ld4(q3 + r3 + c * kF), ld4(p + r3 + c * kF), acc);
+        st4(out + r, acc);
+    }
+}
+
+}  // namespace
+
+extern "C" int nn_ew_mul3(const float* a, const float* b, const float* c, float* out, int64_t n_floats, void* stream) {
+    NN_REQUIRE(a && b && c && out, "null pointer");
+    NN_REQUIRE(n_floats % 4 == 0, "length must be a multiple of 4");
+    if (n_floats <= 0) return 0;
+    const long long n4 = n_floats / 4;
+    long long g = (n4 + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    k_ew_mul3<<<(int)g, 256, 0, (cudaStream_t)stream>>>(a, b, c, out, n4); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_ew_mul3");
+    return 0;
+}
+
+extern "C" int nn_ew_rows(int32_t mode, const float* p, const float* q3, const float* u, float* out, int32_t n_rows, void* stream) {
+    NN_REQUIRE(out != nullptr, "null pointer");
+    NN_REQUIRE(mode >= 0 && mode <= 4, "mode 0..4");
+    if (n_rows <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = nn_ceil_div(n_rows, 8);
+    switch (mode) {
+    case 0: NN_REQUIRE(p && u, "outer needs p, u"); k_ew_rows<0><<<grid, 256, 0, s>>>(p, q3, u, out, n_rows); break;
+    case 1: NN_REQUIRE(q3 && u, "contract_c needs q3, u"); k_ew_rows<1><<<grid, 256, 0, s>>>(p, q3, u, out, n_rows); break;
+    case 2: NN_REQUIRE(q3 && p, "row_dot needs q3, p"); k_ew_rows<2><<<grid, 256, 0, s>>>(p, q3, u, out, n_rows); break;
+    case 3: NN_REQUIRE(q3 && p, "mul_b needs p, q3"); k_ew_rows<3><<<grid, 256, 0, s>>>(p, q3, u, out, n_rows); break;
+    default: NN_REQUIRE(q3 && p, "sum_mul_c needs two [n,3,F] operands"); k_ew_rows<4><<<grid, 256, 0, s>>>(p, q3, u, out, n_rows); break;
+    }
+    NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_ew_rows");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- SiLU family (closed up to the double backward)
+//   mode 0: out = silu(x)          mode 1: out = a * silu'(x)          mode 2: out = a * b * silu''(x)
+// silu' = s (1 + x (1 - s)),  silu'' = s (1 - s) (2 + x (1 - 2 s)),  s = sigmoid(x).  d silu(x) = silu'(x) dx;
+// d [a silu'(x)] = silu'(x) da + a silu''(x) dx: the double backward of an activation is two launches instead of the ~10
+// element-wise ATen kernels autograd composes for it (23 activation sites per training step).
+namespace {
+template <int MODE>
+__global__ void k_ew_silu(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                          float* __restrict__ out, long long n4) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = ld4(x + 4 * t);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float av[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+        if (MODE >= 1) { const float4 t4 = ld4(a + 4 * t); av[0] = t4.x; av[1] = t4.y; av[2] = t4.z; av[3] = t4.w; }
+        if (MODE == 2) { const float4 t4 = ld4(b + 4 * t); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float s = 1.0f / (1.0f + expf(-xs[k]));
+            if (MODE == 0) o[k] = xs[k] * s;
+            else if (MODE == 1) o[k] = av[k] * (s * fmaf(xs[k], 1.0f - s, 1.0f));
+            else o[k] = av[k] * bv[k] * (s * (1.0f - s) * fmaf(xs[k], 1.0f - 2.0f * s, 2.0f));
+        }
+        st4(out + 4 * t, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+}  // namespace
+
+extern "C" int nn_ew_silu(int32_t mode, const float* x, const float* a, const float* b, float* out, int64_t n_floats, void* stream) {
+    NN_REQUIRE(x && out && (mode < 1 || a) && (mode < 2 || b), "null pointer");
+    NN_REQUIRE(mode >= 0 && mode <= 2, "mode 0..2");
+    NN_REQUIRE(n_floats % 4 == 0, "length must be a multiple of 4");
+    if (n_floats <= 0) return 0;
+    const long long n4 = n_floats / 4;
+    long long g = (n4 + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == 0) k_ew_silu<0><<<(int)g, 256, 0, s>>>(x, a, b, out, n4);
+    else if (mode == 1) k_ew_silu<1><<<(int)g, 256, 0, s>>>(x, a, b, out, n4);
+    else k_ew_silu<2><<<(int)g, 256, 0, s>>>(x, a, b, out, n4);
+    NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_ew_silu");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- radial basis with its first two x-derivatives
+// R^k_n(x) = d^k/dx^k [ env(x) sin(f_n x) / x ],  env(x) = (1-x)^3 p(x) = 1 - 55 x^9 + 99 x^10 - 45 x^11  (PolynomialCutoff *
+// RadialBesselLayer, layers/representations.py:166-169,233).  Two kernels closed under differentiation:
+//   rbf_scale(k): out[e,n] = s[e] * R^k_n(x[e])          d/ds = rbf_dot(k)(g),  d/dx = s * rbf_dot(k+1)(g)
+//   rbf_dot(k)  : out[e]   = sum_n g[e,n] R^k_n(x[e])    d/dg = rbf_scale(k)(go), d/dx = go * rbf_dot(k+1)(g)
+// k = 0, 1, 2 (forward, forces, double backward).  At x = 1 (padding rows of the static edge list) env, env' and env''
+// vanish exactly in the factored forms, so padded rows contribute exact zeros at every order.
+namespace {
+__device__ __forceinline__ void rbf_terms(float x, int k, float& e0, float& e1, float& e2) {
+    float p = 45.f;
+    p = fmaf(p, x, 36.f); p = fmaf(p, x, 28.f); p = fmaf(p, x, 21.f); p = fmaf(p, x, 15.f);
+    p = fmaf(p, x, 10.f); p = fmaf(p, x, 6.f); p = fmaf(p, x, 3.f); p = fmaf(p, x, 1.f);
+    const float t = 1.0f - x, x2 = x * x, x4 = x2 * x2, x7 = x4 * x2 * x;
+    e0 = t * t * t * p;
+    e1 = -495.f * x7 * x * t * t;
+    e2 = -495.f * x7 * t * fmaf(-10.f, x, 8.f);
+    (void)k;
+}
+// value of R^k_n at x for frequency f
+__device__ __forceinline__ float rbf_k(float x, float f, int k, float e0, float e1, float e2) {
+    float s, c;
+    sincosf(f * x, &s, &c);
+    const float ix = 1.0f / x;
+    const float sb = s * ix;
+    if (k == 0) return e0 * sb;
+    const float sb1 = (f * x * c - s) * ix * ix;
+    if (k == 1) return fmaf(e1, sb, e0 * sb1);
+    const float sb2 = (-f * f * x * x * s - 2.f * f * x * c + 2.f * s) * ix * ix * ix;
+    return fmaf(e2, sb, fmaf(2.f * e1, sb1, e0 * sb2));
+}
+__global__ void k_rbf_scale(const float* __restrict__ sc, const float* __restrict__ x, const float* __restrict__ freq, int k,
+                            float* __restrict__ out, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * kNB) return;
+    const int e = t / kNB, j = t - e * kNB;
+    const float xv = x[e];
+    float e0, e1, e2;
+    rbf_terms(xv, k, e0, e1, e2);
+    out[t] = (sc ? sc[e] : 1.0f) * rbf_k(xv, freq[j], k, e0, e1, e2);
+}
+__global__ void k_rbf_dot(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ freq, int k,
+                          float* __restrict__ out, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float xv = x[e];
+    float e0, e1, e2;
+    rbf_terms(xv, k, e0, e1, e2);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < kNB; ++j) acc = fmaf(g[(size_t)e * kNB + j], rbf_k(xv, freq[j], k, e0, e1, e2), acc);
+    out[e] = acc;
+}
+}  // namespace
+
+extern "C" int nn_ew_rbf(int32_t op, int32_t k, const float* a, const float* x, const float* freq, float* out, int32_t n_rows, void* stream) {
+    NN_REQUIRE(x && freq && out, "null pointer");
+    NN_REQUIRE(k >= 0 && k <= 2, "derivative order 0..2");
+    NN_REQUIRE(op == 0 || (op == 1 && a), "op 0 = scale (a optional), 1 = dot (a = g required)");
+    if (n_rows <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (op == 0) k_rbf_scale<<<nn_ceil_div((long long)n_rows * kNB, 256), 256, 0, s>>>(a, x, freq, k, out, n_rows);
+    else k_rbf_dot<<<nn_ceil_div(n_rows, 128), 128, 0, s>>>(a, x, freq, k, out, n_rows);
+    NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_ew_rbf");
+    return 0;
+}

@@ -172,6 +172,201 @@ class SegmentSum(torch.autograd.Function):
         return Gather.apply(d_out, ctx.seg), None
 
 
+# ----------------------------------------------------------------------------- fused row products (csrc/train_ops.cu)
+# Six kernels that are closed under differentiation: every backward below is again one of these Functions, so the graph
+# of the double backward consists of them (and of Gemm / GemmTN / Gather / SegmentSum) instead of broadcasting ATen ops.
+def _rows(mode, p, q3, u, out_shape):
+    ref = p if p is not None else q3
+    out = torch.empty(out_shape, dtype=torch.float32, device=ref.device)
+    n = out_shape[0]
+    if n:
+        L.check(L.load().nn_ew_rows(mode, L.ptr(p), L.ptr(q3), L.ptr(u), out.data_ptr(), n, _stream()), 'nn_ew_rows')
+    return out
+
+
+class Mul3(torch.autograd.Function):
+    """a * b * c (same shapes)."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        ctx.save_for_backward(a, b, c)
+        a, b, c = _c(a), _c(b), _c(c)
+        out = torch.empty_like(a)
+        if a.numel():
+            L.check(L.load().nn_ew_mul3(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), a.numel(), _stream()), 'nn_ew_mul3')
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, c = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        return (Mul3.apply(g, b, c) if ni[0] else None, Mul3.apply(g, a, c) if ni[1] else None,
+                Mul3.apply(g, a, b) if ni[2] else None)
+
+
+class Outer(torch.autograd.Function):
+    """out[e,c,:] = x[e,:] * u[e,c];  x [n,F], u [n,3] -> [n,3,F]."""
+
+    @staticmethod
+    def forward(ctx, x, u):
+        ctx.save_for_backward(x, u)
+        return _rows(0, _c(x), None, _c(u), (x.shape[0], 3, x.shape[1]))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, u = ctx.saved_tensors
+        return (ContractC.apply(g, u) if ctx.needs_input_grad[0] else None, RowDot.apply(g, x) if ctx.needs_input_grad[1] else None)
+
+
+class ContractC(torch.autograd.Function):
+    """out[e,:] = sum_c x3[e,c,:] * u[e,c];  x3 [n,3,F], u [n,3] -> [n,F]."""
+
+    @staticmethod
+    def forward(ctx, x3, u):
+        ctx.save_for_backward(x3, u)
+        return _rows(1, None, _c(x3), _c(u), (x3.shape[0], x3.shape[2]))
+
+    @staticmethod
+    def backward(ctx, g):
+        x3, u = ctx.saved_tensors
+        return (Outer.apply(g, u) if ctx.needs_input_grad[0] else None, RowDot.apply(x3, g) if ctx.needs_input_grad[1] else None)
+
+
+class RowDot(torch.autograd.Function):
+    """out[e,c] = <x3[e,c,:], x[e,:]>;  x3 [n,3,F], x [n,F] -> [n,3]."""
+
+    @staticmethod
+    def forward(ctx, x3, x):
+        ctx.save_for_backward(x3, x)
+        return _rows(2, _c(x), _c(x3), None, (x3.shape[0], 3))
+
+    @staticmethod
+    def backward(ctx, g):
+        x3, x = ctx.saved_tensors
+        return (Outer.apply(x, g) if ctx.needs_input_grad[0] else None, ContractC.apply(x3, g) if ctx.needs_input_grad[1] else None)
+
+
+class MulB(torch.autograd.Function):
+    """out[e,c,:] = x[e,:] * y3[e,c,:];  x [n,F], y3 [n,3,F] -> [n,3,F]."""
+
+    @staticmethod
+    def forward(ctx, x, y3):
+        ctx.save_for_backward(x, y3)
+        return _rows(3, _c(x), _c(y3), None, tuple(y3.shape))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y3 = ctx.saved_tensors
+        return (SumMulC.apply(g, y3) if ctx.needs_input_grad[0] else None, MulB.apply(x, g) if ctx.needs_input_grad[1] else None)
+
+
+class SumMulC(torch.autograd.Function):
+    """out[e,:] = sum_c x3[e,c,:] * y3[e,c,:];  [n,3,F] x [n,3,F] -> [n,F]."""
+
+    @staticmethod
+    def forward(ctx, x3, y3):
+        ctx.save_for_backward(x3, y3)
+        return _rows(4, _c(y3), _c(x3), None, (x3.shape[0], x3.shape[2]))
+
+    @staticmethod
+    def backward(ctx, g):
+        x3, y3 = ctx.saved_tensors
+        return (MulB.apply(g, y3) if ctx.needs_input_grad[0] else None, MulB.apply(g, x3) if ctx.needs_input_grad[1] else None)
+
+
+def _rbf_raw(op, k, a, x, freq):
+    if k > 2:
+        raise NotImplementedError('third-order differentiation through the radial basis is not implemented by the fused training kernels')
+    x = _c(x)
+    n = x.shape[0]
+    out = torch.empty((n, L.NN_NB) if op == 0 else (n, 1), dtype=torch.float32, device=x.device)
+    if n:
+        L.check(L.load().nn_ew_rbf(op, k, L.ptr(None if a is None else _c(a)), x.data_ptr(), freq.data_ptr(), out.data_ptr(), n, _stream()),
+                'nn_ew_rbf')
+    return out
+
+
+class RbfScale(torch.autograd.Function):
+    """out[e,n] = s[e] * R^k_n(x[e]);  s, x [E,1] -> [E,20]  (R^k = k-th x-derivative of env(x) sin(f_n x) / x)."""
+
+    @staticmethod
+    def forward(ctx, s, x, freq, k):
+        ctx.save_for_backward(s, x, freq)
+        ctx.k = k
+        return _rbf_raw(0, k, s, x, freq)
+
+    @staticmethod
+    def backward(ctx, g):
+        s, x, freq = ctx.saved_tensors
+        ds = RbfDot.apply(g, x, freq, ctx.k) if ctx.needs_input_grad[0] else None
+        dx = s * RbfDot.apply(g, x, freq, ctx.k + 1) if ctx.needs_input_grad[1] else None
+        return ds, dx, None, None
+
+
+class RbfDot(torch.autograd.Function):
+    """out[e] = sum_n g[e,n] R^k_n(x[e]);  g [E,20], x [E,1] -> [E,1]."""
+
+    @staticmethod
+    def forward(ctx, g, x, freq, k):
+        ctx.save_for_backward(g, x, freq)
+        ctx.k = k
+        return _rbf_raw(1, k, g, x, freq)
+
+    @staticmethod
+    def backward(ctx, go):
+        g, x, freq = ctx.saved_tensors
+        dg = RbfScale.apply(go, x, freq, ctx.k) if ctx.needs_input_grad[0] else None
+        dx = go * RbfDot.apply(g, x, freq, ctx.k + 1) if ctx.needs_input_grad[1] else None
+        return dg, dx, None, None
+
+
+def _silu_raw(mode, x, a=None, b=None):
+    x = _c(x)
+    out = torch.empty_like(x)
+    if x.numel():
+        L.check(L.load().nn_ew_silu(mode, x.data_ptr(), L.ptr(None if a is None else _c(a)), L.ptr(None if b is None else _c(b)),
+                                    out.data_ptr(), x.numel(), _stream()), 'nn_ew_silu')
+    return out
+
+
+class Silu(torch.autograd.Function):
+    """silu(x); backward SiluB, whose backward is SiluB again and one silu'' kernel (never differentiated further)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return _silu_raw(0, x)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return SiluB.apply(g, x)
+
+
+class SiluB(torch.autograd.Function):
+    """g * silu'(x)."""
+
+    @staticmethod
+    def forward(ctx, g, x):
+        ctx.save_for_backward(g, x)
+        return _silu_raw(1, x, g)
+
+    @staticmethod
+    def backward(ctx, go):
+        g, x = ctx.saved_tensors
+        if torch.is_grad_enabled() and ctx.needs_input_grad[1]:
+            # this backward is itself being recorded (create_graph in the SECOND backward): third derivatives of the
+            # activation would be needed - the reference's training step never asks for them (trainer.py:303-313)
+            raise NotImplementedError('third-order differentiation through SiLU is not implemented by the fused training kernels')
+        dg = SiluB.apply(go, x) if ctx.needs_input_grad[0] else None
+        dx = _silu_raw(2, x, go, g) if ctx.needs_input_grad[1] else None       # go * g * silu''(x)
+        return dg, dx
+
+
+def silu(x):
+    return Silu.apply(x)
+
+
 def linear(x, weight, bias=None):
     """x @ weight^T (+ bias) through the tensor-core GEMM."""
     y = Gemm.apply(x, weight.t())
@@ -179,14 +374,6 @@ def linear(x, weight, bias=None):
 
 
 # ----------------------------------------------------------------------------- forward (training mode)
-def _envelope(x):
-    # 1 - 55x^9 + 99x^10 - 45x^11 in the factored form used by csrc/pair_ops.cu
-    p = torch.zeros_like(x) + 45.0
-    for c in (36.0, 28.0, 21.0, 15.0, 10.0, 6.0, 3.0, 1.0):
-        p = p * x + c
-    return (1.0 - x) ** 3 * p
-
-
 def _edges(nl, pos, N, static):
     """Directed edges (reference order) and their minimum-image displacements as a function of pos.
 
@@ -257,31 +444,31 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     x = d / cutoff
     emb = model.embedding_layers
     freq = emb.edge_embedding.embedding.frequencies
-    rbf = _envelope(x) * torch.sin(freq * x) / x
+    rbf = RbfScale.apply(torch.ones_like(x), x, freq.detach().to(torch.float32).contiguous(), 0)
     rbf_pad = Fn.pad(rbf, (0, F - rbf.shape[1]))
     a = Fn.embedding(z, emb.node_embedding.weight, padding_idx=0)
     f = torch.zeros(N, 3 * F, dtype=torch.float32, device=dev)
     for layer in model.interaction_layers:
         n0, n2 = layer.message_nodepart[0], layer.message_nodepart[2]
-        mn = linear(Fn.silu(linear(a, n0.weight, n0.bias)), n2.weight, n2.bias)
+        mn = linear(silu(linear(a, n0.weight, n0.bias)), n2.weight, n2.bias)
         # K = 20 contraction through the same fp32-faithful GEMM (zero-padded to K = 128): a library matmul may
         # silently run in single-pass TF32 (TORCH_ALLOW_TF32_CUBLAS_OVERRIDE), which breaks gradient parity
         me = Gemm.apply(rbf_pad, Fn.pad(layer.message_edgepart.weight.t(), (0, 0, 0, F - rbf.shape[1])))
-        m = me * Gather.apply(mn, seg_dst) * Gather.apply(mn, seg_src)
+        m = Mul3.apply(me, Gather.apply(mn, seg_dst), Gather.apply(mn, seg_src))
         a = a + SegmentSum.apply(m, seg_dst)
-        e1 = linear(Fn.silu(linear(m, layer.equiv_message1[0].weight)), layer.equiv_message1[2].weight)
-        e2 = linear(Fn.silu(linear(m, layer.equiv_message2[0].weight)), layer.equiv_message2[2].weight)
+        e1 = linear(silu(linear(m, layer.equiv_message1[0].weight)), layer.equiv_message1[2].weight)
+        e2 = linear(silu(linear(m, layer.equiv_message2[0].weight)), layer.equiv_message2[2].weight)
         fj = Gather.apply(f, seg_src).view(-1, 3, F)
-        vec = e1.unsqueeze(1) * u.unsqueeze(2) + e2.unsqueeze(1) * fj
+        vec = Outer.apply(e1, u) + MulB.apply(e2, fj)
         f = f + SegmentSum.apply(vec.reshape(-1, 3 * F), seg_dst)
         g = linear(f.view(3 * N, F), layer.equiv_update.weight).view(N, 3, F)
-        a = a + (f.view(N, 3, F) * g).sum(1)
+        a = a + SumMulC.apply(f.view(N, 3, F), g)
         if layer.layer_norm is not None:
             a = Fn.layer_norm(a, (F,), layer.layer_norm.weight, layer.layer_norm.bias, layer.layer_norm.eps)
     k = props.index('energy')
     head, scaler = model.output_layers[k].layers, model.scalers[k]
-    h = Fn.silu(linear(a, head[0].weight, head[0].bias))
-    h = Fn.silu(linear(h, head[2].weight, head[2].bias))
+    h = silu(linear(a, head[0].weight, head[0].bias))
+    h = silu(linear(h, head[2].weight, head[2].bias))
     o = (h * head[4].weight).sum(1, keepdim=True) + head[4].bias           # 128 -> 1: exact fp32 reduction
     e_atom = o * scaler.scale(z) + scaler.shift(z)
     energy = torch.zeros(cell.shape[0], dtype=torch.float32, device=dev).index_add(0, batch, e_atom.reshape(-1))
@@ -293,9 +480,9 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
         elif key == 'direct_force':
             kd = props.index(key)
             dl, ds = model.output_layers[kd].layers, model.scalers[kd]
-            hd = Fn.silu(linear(a, dl[0].weight, dl[0].bias))
-            hd = linear(Fn.silu(linear(hd, dl[2].weight, dl[2].bias)), dl[4].weight, dl[4].bias)
-            out.direct_force = (hd.unsqueeze(1) * f.view(N, 3, F)).sum(-1) * ds.scale(z)
+            hd = silu(linear(a, dl[0].weight, dl[0].bias))
+            hd = linear(silu(linear(hd, dl[2].weight, dl[2].bias)), dl[4].weight, dl[4].bias)
+            out.direct_force = RowDot.apply(f.view(N, 3, F), hd) * ds.scale(z)
         elif key == 'hessian':
             # reference models/output.py:141-152 (vmap over unit vectors): one reverse pass per row of the 3N x 3N matrix
             if not hasattr(out, 'pos_grad') or not out.pos_grad.requires_grad:
@@ -325,28 +512,29 @@ def allreduce_gradients(params, group=None, flags=None):
     params = [p for p in params if p.requires_grad]
     if not params:
         return None
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:                       # nothing to average: leave the gradients (and the flags) where they are
+        return None
     parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params]
     n_flags = 0 if flags is None else flags.numel()
     if n_flags:
         parts.append(flags.reshape(-1).to(parts[0].dtype))
     flat = torch.cat(parts)
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world > 1:
-        dist.all_reduce(flat, group=group)
-        if n_flags:
-            flags.copy_(flat[-n_flags:].reshape(flags.shape))
-        flat /= world
+    dist.all_reduce(flat, group=group)
     if n_flags:
+        flags.copy_(flat[-n_flags:].reshape(flags.shape))
         flat = flat[:-n_flags]
-    off = 0
+    flat /= world
+    # one fused copy back into the parameters' gradient tensors
+    views, off = [], 0
     for p in params:
         n = p.numel()
-        g = flat[off:off + n].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
+        views.append(flat[off:off + n].view_as(p))
         off += n
+    missing = [i for i, p in enumerate(params) if p.grad is None]
+    for i in missing:
+        params[i].grad = torch.empty_like(params[i])
+    torch._foreach_copy_([p.grad for p in params], views)
     return flat
 
 

@@ -688,3 +688,73 @@ def test_ase_calculator_resident_md_path(tmp_path):
         for m in (calc.model, ref.model):
             m.scalers[0].shift.weight.add_(0.5)
     both(z, pos, cell)                                         # parameter update is picked up
+
+
+def test_fused_row_products_double_backward():
+    """Mul3 / Outer / ContractC / RowDot / MulB / SumMulC (csrc/train_ops.cu): values, gradients and gradients of gradients
+    against the broadcasting torch expressions they replace, in fp64."""
+    from newtonnet_b200.train import ContractC, Mul3, MulB, Outer, RowDot, SumMulC
+
+    def run(mine, dt):
+        g = torch.Generator().manual_seed(3)
+        n = 257
+        r = lambda *sh: torch.randn(*sh, generator=g).to(dev(), dt).requires_grad_(True)
+        a, b, c, x, u, y3, z3, tgt = r(n, 128), r(n, 128), r(n, 128), r(n, 128), r(n, 3), r(n, 3, 128), r(n, 3, 128), r(n, 128)
+        if mine:
+            m = Mul3.apply(a, b, c)
+            vec = Outer.apply(x, u) + MulB.apply(m, y3)
+            s = SumMulC.apply(vec, z3) + ContractC.apply(vec, u)
+            d = RowDot.apply(vec, m)
+        else:
+            m = a * b * c
+            vec = x.unsqueeze(1) * u.unsqueeze(2) + m.unsqueeze(1) * y3
+            s = (vec * z3).sum(1) + (vec * u.unsqueeze(2)).sum(1)
+            d = (vec * m.unsqueeze(1)).sum(-1)
+        e = (s * s).sum() + (d ** 3).sum() * 1e-3
+        leaves = [a, b, c, x, u, y3, z3]
+        g1 = torch.autograd.grad(e, [x, u, y3], create_graph=True)
+        loss = ((g1[0] - tgt) ** 2).mean() + (g1[1] ** 2).mean() + (g1[2] ** 2).mean() * 1e-2
+        g2 = torch.autograd.grad(loss, leaves, allow_unused=True)
+        outs = [s, d] + list(g1) + [t for t in g2 if t is not None]
+        return [t.detach().double().cpu() for t in outs]
+
+    for got, ref in zip(run(True, torch.float32), run(False, torch.float64)):
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)) < 2e-5
+
+
+def test_fused_radial_basis_and_silu_double_backward():
+    """RbfScale / RbfDot (env(x) sin(f x)/x with two x-derivatives) and Silu / SiluB against the torch expressions in fp64:
+    value, gradient, gradient of the gradient; exact zeros at x = 1 (padding rows)."""
+    import math
+    from newtonnet_b200.train import RbfScale, silu
+    freq32 = torch.tensor([np.float32(n * math.pi) for n in range(1, 21)], device=dev())
+
+    def env(x):
+        p = torch.zeros_like(x) + 45.0
+        for c in (36.0, 28.0, 21.0, 15.0, 10.0, 6.0, 3.0, 1.0):
+            p = p * x + c
+        return (1.0 - x) ** 3 * p
+
+    def run(mine, dt):
+        g = torch.Generator().manual_seed(9)
+        n = 333
+        x = (torch.rand(n, 1, generator=g) * 0.9 + 0.08).to(dev(), dt).requires_grad_(True)
+        w = torch.randn(n, 20, generator=g).to(dev(), dt).requires_grad_(True)
+        h = torch.randn(n, 128, generator=g).to(dev(), dt).requires_grad_(True)
+        f = freq32.to(dt)
+        rbf = RbfScale.apply(torch.ones_like(x), x, freq32, 0) if mine else env(x) * torch.sin(f * x) / x
+        act = silu(h) if mine else torch.nn.functional.silu(h)
+        e = (rbf * w).sum() + (rbf ** 2).sum() + (act ** 2).sum()
+        gx, gh = torch.autograd.grad(e, [x, h], create_graph=True)
+        loss = (gx ** 2).sum() + (gh ** 3).sum()
+        g2 = torch.autograd.grad(loss, [x, w, h])
+        return [t.detach().double().cpu() for t in (rbf, act, gx, gh) + tuple(g2)]
+
+    for got, ref in zip(run(True, torch.float32), run(False, torch.float64)):
+        assert float((got - ref).abs().max() / ref.abs().max()) < 5e-5
+    one = torch.ones(4, 1, device=dev(), requires_grad=True)
+    r = RbfScale.apply(torch.ones_like(one), one, freq32, 0)
+    g1, = torch.autograd.grad(r.sum(), one, create_graph=True)
+    g2, = torch.autograd.grad(g1.sum(), one)
+    assert float(r.abs().max()) == 0.0 and float(g1.abs().max()) == 0.0 and float(g2.abs().max()) == 0.0
