@@ -625,7 +625,8 @@ class DomainDecomposition:
 
         # ---- neighbour list over owned + ghost atoms (ghost-ghost pairs dropped); capacities are kept
         def build(cap):
-            nl = NeighborList(engine, pos_l, cell_l, batch_l, cap_edges=cap)
+            # ghost rows of the list stay empty, so an owned-ghost pair has ONE directed edge: up to one pair per edge
+            nl = NeighborList(engine, pos_l, cell_l, batch_l, cap_edges=cap, cap_pairs=cap)
             nl.struct.n_owned = n_owned
             return nl
 
