@@ -144,6 +144,10 @@ NN_API size_t nn_nbr_workspace_bytes(int32_t n_atoms, int32_t n_systems);
 NN_API int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream);
 /* pass 2: fills col / edge_pair / pair_*; entries beyond the capacities are dropped and flagged. */
 NN_API int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream);
+/* rev[e] = position of the reversed edge (j, i) of directed edge e = (i, j), rev [cap_edges]: read in row order it lists
+ * the edges grouped by SOURCE atom (the transposed adjacency of the symmetric edge set), which is what the scatter to the
+ * source atoms of the training path needs (models/newtonnet.py:211 mn[edge_index[1]] under autograd). */
+NN_API int nn_nbr_edge_reverse(const nn_nbr* nl, int32_t* rev, void* stream);
 /* edge_index [2,E] int64 in the reference's order (representations.py:74-82,97). */
 NN_API int nn_nbr_edge_index(const nn_nbr* nl, int64_t* edge_index, int64_t n_edges, void* stream);
 

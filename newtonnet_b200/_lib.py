@@ -91,6 +91,7 @@ SYMBOLS = {
     'nn_nbr_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'nn_nbr_count': (C.c_int, [C.POINTER(Nbr), C.c_float, _fp]),
     'nn_nbr_fill': (C.c_int, [C.POINTER(Nbr), C.c_float, _fp]),
+    'nn_nbr_edge_reverse': (C.c_int, [C.POINTER(Nbr), _fp, _fp]),
     'nn_nbr_edge_index': (C.c_int, [C.POINTER(Nbr), _fp, C.c_int64, _fp]),
     'nn_gemm128': (C.c_int, [C.POINTER(GemmArgs), _fp]),
     'nn_gemm128_prepare_b': (C.c_int, [_fp, _fp, _fp]),

@@ -65,6 +65,7 @@ static inline void nn_launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+int nn_num_sms();           // multiprocessor count of the current device (cached per device; 148 on B200)
 static inline int nn_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t nn_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

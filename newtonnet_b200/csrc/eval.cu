@@ -65,6 +65,19 @@ bool nn_pdl_enabled() {
     return v == 1;
 }
 
+int nn_num_sms() {
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
+    }
+    return sms[dev];
+}
+
 bool nn_pdl_all_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("NN_PDL_ALL"); v = (e && e[0] == '1' && nn_pdl_enabled()) ? 1 : 0; }

@@ -54,16 +54,20 @@ k_gemm_tn_tc(const float* __restrict__ X, const float* __restrict__ Y, int M, in
         // ===================== producers: 32-row blocks of X and Y -> transposed hi / lo tiles =====================
         const int col = threadIdx.x & 127, half = threadIdx.x >> 7;          // chunks 4*half .. 4*half+3 (rows 16*half .. +15)
         uint32_t stage = 0, phase = 0;
-        for (int b = 0; b < n_blocks; ++b) {
+        float xv[16], yv[16], xn[16], yn[16];
+        auto load = [&](int b, float (&xo)[16], float (&yo)[16]) {
             const int r0 = r_begin + b * KB + 16 * half;
-            float xv[16], yv[16];
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
                 const int r = r0 + t;
-                const bool ok = r < r_end;
-                xv[t] = ok ? X[(size_t)r * 128 + col] : 0.f;
-                yv[t] = ok ? Y[(size_t)r * 128 + col] : 0.f;
+                const bool ok = b < n_blocks && r < r_end;
+                xo[t] = ok ? X[(size_t)r * 128 + col] : 0.f;
+                yo[t] = ok ? Y[(size_t)r * 128 + col] : 0.f;
             }
+        };
+        load(0, xv, yv);
+        for (int b = 0; b < n_blocks; ++b) {
+            load(b + 1, xn, yn);                 // the next block's rows are in flight while this one is split and stored
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             uint8_t* st = smem_gen + (sT - base) + stage * STAGE_BYTES;
 #pragma unroll
@@ -81,6 +85,8 @@ k_gemm_tn_tc(const float* __restrict__ X, const float* __restrict__ Y, int M, in
             fence_proxy_async();
             mbar_arrive(bar_full + 8 * stage);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) { xv[t] = xn[t]; yv[t] = yn[t]; }
         }
     } else if (lane == 0) {
         // ===================== MMA issue =====================
@@ -156,11 +162,12 @@ bool g_attr = false;
 
 }  // namespace
 
-// number of CTAs (= partials) for m rows: at least 16 row blocks of 32 per CTA (a CTA's fixed cost - barriers, tensor
-// memory, the partial's write and its read by the reduction - is worth several row blocks), at most one CTA per SM
+// number of CTAs (= partials) for m rows: at least 6 row blocks of 32 per CTA, at most one CTA per SM (measured at 30k
+// rows: 4 blocks per CTA 16 + 16 us (kernel + reduction), 16 blocks per CTA 29 + 9 us without the register prefetch)
 int nn_gemm_tn_tc_ctas(int m) {
-    int b = nn_ceil_div(m, 16 * tc::KB);
-    return b < 1 ? 1 : (b > 148 ? 148 : b);
+    int b = nn_ceil_div(m, 6 * tc::KB);
+    const int sms = nn_num_sms();
+    return b < 1 ? 1 : (b > sms ? sms : b);
 }
 
 int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, cudaStream_t s) {

@@ -7,7 +7,6 @@
 // work is HBM/latency-bound integer + fp32 work: warp per atom, coalesced candidate reads, no atomics
 // on the output (two-pass count / fill), rows sorted by source index so the order equals the
 // reference's (i-major, j ascending).
-#include <cub/device/device_scan.cuh>
 #include "common.cuh"
 
 namespace {
@@ -28,10 +27,64 @@ struct NbrWs {
     size_t total;
 };
 
+// ---------------------------------------------------------------- exclusive prefix sum (int32)
+// Tiles of 4096 elements: one 1024-thread block scans a tile (4 elements per thread, warp shuffles, one shared-memory hop)
+// and emits the tile total; totals are scanned by the same kernel one level up and added back.  One launch for
+// n <= 4096 (every list of a small system), three for up to 16.7 M elements.
+constexpr int kScanTile = 4096;
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                     int* __restrict__ tile_total) {
+    __shared__ int s_warp[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = base + k < n ? in[base + k] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        s_warp[lane] = wi - w;                  // exclusive prefix of the warp totals
+        if (lane == 31 && tile_total) tile_total[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int run = s_warp[wid] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+__global__ void k_scan_add(int* __restrict__ out, int n, const int* __restrict__ tile_prefix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_prefix[i / kScanTile];
+}
 size_t scan_temp_bytes(int n) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, n);
-    return bytes;
+    size_t ints = 0;
+    for (int m = nn_ceil_div(n, kScanTile); m > 1; m = nn_ceil_div(m, kScanTile)) ints += (size_t)m;
+    return (ints + 1) * sizeof(int);
+}
+// out may alias in.  Returns the number of kernels launched.
+int exclusive_scan(const int* in, int* out, int n, int* tmp, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int tiles = nn_ceil_div(n, kScanTile);
+    if (tiles == 1) { k_scan_tiles<<<1, 1024, 0, s>>>(in, out, n, nullptr); return 1; }
+    k_scan_tiles<<<tiles, 1024, 0, s>>>(in, out, n, tmp);
+    int launched = 1 + exclusive_scan(tmp, tmp, tiles, tmp + tiles, s);
+    k_scan_add<<<nn_ceil_div(n, 256), 256, 0, s>>>(out, n, tmp);
+    return launched + 1;
 }
 
 NbrWs carve(void* base, size_t cap, int N, int B) {
@@ -508,6 +561,23 @@ __global__ void k_edge_index(const int* __restrict__ row_ptr, const int* __restr
     }
 }
 
+// rev[e] = index of the reversed edge (j, i) of edge e = (i, j): binary search of i in the (sorted) row of j.  Grouping the
+// edges by SOURCE atom is then rev read in row order - the transposed adjacency without a sort (the edge set is symmetric).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_edge_reverse(const int* __restrict__ row_ptr, const int* __restrict__ col, int N, int cap_edges, const int* __restrict__ status,
+               int* __restrict__ rev) {
+    if (status[NN_ST_EDGE_OVERFLOW] != 0) return;
+    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1] && e < cap_edges; e += 32) {
+        const int j = col[e];
+        int lo = row_ptr[j], hi = row_ptr[j + 1];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < i) lo = mid + 1; else hi = mid; }
+        rev[e] = lo;
+    }
+}
+
 }  // namespace
 
 const SysMeta* nn_nbr_sysmeta(const nn_nbr* nl) { return (const SysMeta*)nl->workspace; }
@@ -541,20 +611,18 @@ extern "C" int nn_nbr_count(const nn_nbr* nl, float cutoff, void* stream) {
     k_bounds_init<<<nn_ceil_div(B * 6, 256), 256, 0, s>>>(w.bounds, B); NN_LAUNCHED(1);
     if (N > 0) { k_sys_bounds<<<nn_ceil_div(N, 256), 256, 0, s>>>(nl->pos, nl->batch, N, B, w.bounds); NN_LAUNCHED(1); }
     k_sys_plan<<<1, 1024, 0, s>>>(nl->cell, nl->sys_ptr, w.bounds, B, cutoff, w.meta, nl->status); NN_LAUNCHED(1);
-    NN_CHECK_LAUNCH("nn_nbr_count(plan)");      // the library scans below clear a pending launch error
+    NN_CHECK_LAUNCH("nn_nbr_count(plan)");      // checked per launch group so that a failed launch is reported where it happened
     if (N > 0) {
         k_bin_count<<<nn_ceil_div(N, 256), 256, 0, s>>>(nl->pos, nl->batch, N, w.meta, w.atom_cell, w.cell_count); NN_LAUNCHED(1);
         NN_CHECK_LAUNCH("nn_nbr_count(bin)");
-        size_t tb = w.scan_tmp_bytes;
-        cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.cell_count, w.cell_start, cap_cells + 1, s); NN_LAUNCHED(2);
+        NN_LAUNCHED(exclusive_scan(w.cell_count, w.cell_start, cap_cells + 1, (int*)w.scan_tmp, s));
         k_bin_fill<<<nn_ceil_div(N, 256), 256, 0, s>>>(N, w.atom_cell, w.cell_start, w.cell_fill, w.sorted_atoms); NN_LAUNCHED(1);
         k_nbr_count<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
             nl->pos, nl->batch, N, w.meta, w.cell_start, w.sorted_atoms, cutoff, nl->n_owned > 0 ? nl->n_owned : N, w.deg,
             nl->status); NN_LAUNCHED(1);
         NN_CHECK_LAUNCH("nn_nbr_count(count)");
     }
-    size_t tb = w.scan_tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.deg, nl->row_ptr, N + 1, s); NN_LAUNCHED(2);
+    NN_LAUNCHED(exclusive_scan(w.deg, nl->row_ptr, N + 1, (int*)w.scan_tmp, s));
     k_finish_count<<<1, 1, 0, s>>>(nl->row_ptr, N, nl->cap_edges, nl->status); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_nbr_count");
     return 0;
@@ -574,8 +642,7 @@ extern "C" int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream) {
             nl->col, w.fwd_cnt, nl->status); NN_LAUNCHED(1);
         NN_CHECK_LAUNCH("nn_nbr_fill(fill)");
     }
-    size_t tb = w.scan_tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, w.fwd_cnt, nl->pair_ptr, N + 1, s); NN_LAUNCHED(2);
+    NN_LAUNCHED(exclusive_scan(w.fwd_cnt, nl->pair_ptr, N + 1, (int*)w.scan_tmp, s));
     k_finish_pairs<<<1, 1, 0, s>>>(nl->pair_ptr, N, nl->cap_pairs, nl->status); NN_LAUNCHED(1);
     if (N > 0) {
         k_pair_build<<<nn_ceil_div(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
@@ -583,6 +650,15 @@ extern "C" int nn_nbr_fill(const nn_nbr* nl, float cutoff, void* stream) {
             nl->pair_i, nl->pair_j, nl->pair_disp, nl->status); NN_LAUNCHED(1);
     }
     NN_CHECK_LAUNCH("nn_nbr_fill");
+    return 0;
+}
+
+extern "C" int nn_nbr_edge_reverse(const nn_nbr* nl, int32_t* rev, void* stream) {
+    NN_REQUIRE(nl && rev && nl->row_ptr && nl->col, "null pointer");
+    if (nl->n_atoms == 0) return 0;
+    k_edge_reverse<<<nn_ceil_div(nl->n_atoms, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        nl->row_ptr, nl->col, nl->n_atoms, nl->cap_edges, nl->status, rev); NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_nbr_edge_reverse");
     return 0;
 }
 

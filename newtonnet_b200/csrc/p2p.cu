@@ -266,7 +266,7 @@ extern "C" int nn_dd_halo_push(const nn_dd_comm* c, int32_t channel, int32_t seq
         NN_REQUIRE(p.flags && (p.send_end == p.send_begin || (p.landing[0] && p.landing[1])), "peer memory not mapped");
     }
     const long long total = (long long)last_end * (width / 4);
-    k_halo_push<<<grid_for(total, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(rows, c->send_idx, width / 4, a, c->step,
+    k_halo_push<<<grid_for(total, 256, nn_num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(rows, c->send_idx, width / 4, a, c->step,
                                                                                  c->done + channel); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_dd_halo_push");
     return 0;
@@ -276,7 +276,7 @@ extern "C" int nn_dd_halo_wait(const nn_dd_comm* c, int32_t channel, int32_t seq
     if (int rc = check_comm(c, channel)) return rc;
     NN_REQUIRE(width > 0 && width % 4 == 0 && width <= NN_DD_MAX_WIDTH, "width must be a multiple of 4, at most 384");
     const long long n4 = (long long)c->n_ghost * (width / 4);
-    k_halo_wait_copy<<<grid_for(n4, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(
+    k_halo_wait_copy<<<grid_for(n4, 256, nn_num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(
         c->flags[channel], c->world, c->rank, c->step, c->stride[channel], seq, c->landing[channel][0], c->landing[channel][1],
         ghost_rows, n4, c->status); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_dd_halo_wait");
@@ -299,10 +299,10 @@ extern "C" int nn_dd_finish(const nn_dd_comm* c, int32_t seq, const float* force
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long long total = (long long)c->n_owned * c->world;
-    k_dd_push_results<<<grid_for(total, 256, 148 * 2), 256, 0, s>>>(forces_owned, l2g, c->n_owned, energy, virial, stress,
+    k_dd_push_results<<<grid_for(total, 256, nn_num_sms() * 2), 256, 0, s>>>(forces_owned, l2g, c->n_owned, energy, virial, stress,
                                                                     nbr_status, c->status, a, c->step, c->done); NN_LAUNCHED(1);
     const long long n3 = (long long)c->n_atoms_total * 3;
-    k_dd_finish<<<grid_for(n3, 256, 148 * 2), 256, 0, s>>>(c->flags[0], c->world, c->rank, c->step, c->stride[0], seq, c->partials,
+    k_dd_finish<<<grid_for(n3, 256, nn_num_sms() * 2), 256, 0, s>>>(c->flags[0], c->world, c->rank, c->step, c->stride[0], seq, c->partials,
                                                            c->forces_full, n3, forces_out, out_small, c->status, out_status); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_dd_finish");
     return 0;

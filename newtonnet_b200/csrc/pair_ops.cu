@@ -693,7 +693,7 @@ __global__ void k_halo_pack(const float* __restrict__ src, const int* __restrict
 
 int grid_for_rows(long long rows) {
     long long g = (rows + kWarps - 1) / kWarps;
-    const long long cap = 148LL * 16;
+    const long long cap = (long long)nn_num_sms() * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -703,7 +703,7 @@ int grid_for_rows(long long rows) {
 extern "C" int nn_edge_geom_fwd(const float* pair_disp, const float* freq, float cutoff, const int32_t* n_pairs_dev,
                                 int32_t cap_pairs, float* rbf, float* drbf, float* unit, float* dist, void* stream) {
     if (cap_pairs <= 0) return 0;
-    int grid = min(nn_ceil_div((long long)cap_pairs * 5, 320), 148 * 6);
+    int grid = min(nn_ceil_div((long long)cap_pairs * 5, 320), nn_num_sms() * 6);
     nn_launch_dep(k_edge_geom_fwd, dim3(grid), dim3(320), 0, (cudaStream_t)stream, pair_disp, freq, cutoff, n_pairs_dev, cap_pairs, rbf, drbf, unit, dist); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_fwd");
     return 0;
@@ -713,7 +713,7 @@ extern "C" int nn_edge_geom_bwd(const float* x_bar, int32_t n_slots, const float
                                 const float* dist, float cutoff, const int32_t* n_pairs_dev, int32_t cap_pairs,
                                 float* disp_bar, void* stream) {
     if (cap_pairs <= 0) return 0;
-    int grid = min(nn_ceil_div(cap_pairs, 256), 148 * 8);
+    int grid = min(nn_ceil_div(cap_pairs, 256), nn_num_sms() * 8);
     nn_launch_dep(k_edge_geom_bwd, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x_bar, n_slots, unit_bar, unit, dist, cutoff, n_pairs_dev, cap_pairs,
                                                            disp_bar); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_edge_geom_bwd");
@@ -822,7 +822,7 @@ extern "C" int nn_halo_pack(const float* src, const int32_t* idx, int32_t n, int
     NN_REQUIRE(width > 0 && width % 4 == 0, "width must be a positive multiple of 4");
     if (n <= 0) return 0;
     long long total = (long long)n * (width / 4);
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    int grid = (int)((total + 255) / 256); if (grid > nn_num_sms() * 16) grid = nn_num_sms() * 16;
     k_halo_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(src, idx, n, width / 4, out); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_halo_pack");
     return 0;

@@ -197,7 +197,7 @@ extern "C" int nn_ew_mul3(const float* a, const float* b, const float* c, float*
     NN_REQUIRE(n_floats % 4 == 0, "length must be a multiple of 4");
     if (n_floats <= 0) return 0;
     const long long n4 = n_floats / 4;
-    long long g = (n4 + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    long long g = (n4 + 255) / 256; if (g > nn_num_sms() * 16) g = nn_num_sms() * 16;
     k_ew_mul3<<<(int)g, 256, 0, (cudaStream_t)stream>>>(a, b, c, out, n4); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_ew_mul3");
     return 0;
@@ -254,7 +254,7 @@ extern "C" int nn_ew_silu(int32_t mode, const float* x, const float* a, const fl
     NN_REQUIRE(n_floats % 4 == 0, "length must be a multiple of 4");
     if (n_floats <= 0) return 0;
     const long long n4 = n_floats / 4;
-    long long g = (n4 + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    long long g = (n4 + 255) / 256; if (g > nn_num_sms() * 16) g = nn_num_sms() * 16;
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == 0) k_ew_silu<0><<<(int)g, 256, 0, s>>>(x, a, b, out, n4);
     else if (mode == 1) k_ew_silu<1><<<(int)g, 256, 0, s>>>(x, a, b, out, n4);

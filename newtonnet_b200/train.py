@@ -133,6 +133,16 @@ class Segments:
         else:
             self.perm = torch.sort(idx, stable=True).indices.to(torch.int32).contiguous()
 
+    @classmethod
+    def from_csr(cls, idx, n_rows, row_ptr, perm=None):
+        """Segments whose grouping is already known (the neighbour list's CSR): no counting pass, no sort."""
+        self = cls.__new__(cls)
+        self.idx = idx.to(torch.int32).contiguous()
+        self.n_rows = int(n_rows)
+        self.row_ptr = row_ptr
+        self.perm = perm
+        return self
+
 
 class Gather(torch.autograd.Function):
     """out[k,:] = rows[idx[k],:]  (width % 4 == 0)."""
@@ -437,8 +447,14 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
         pad = torch.cat([torch.full((1, 1), float(cutoff), dtype=torch.float32, device=dev),
                          torch.zeros(1, 2, dtype=torch.float32, device=dev)], 1)      # fill kernels: no H2D copy while capturing
         disp = torch.where(valid.unsqueeze(1), disp, pad)
-    seg_dst = Segments(dst, N, grouped=True, valid=valid)
-    seg_src = Segments(src, N, grouped=False if static else None, valid=valid)
+    # segments straight from the neighbour list: rows of the destination-sorted CSR, and - the edge set being symmetric -
+    # the same rows read through the reversed-edge map for the grouping by source atom (no counting pass, no sort); a
+    # list that outgrew its capacity exposes empty segments
+    rev = torch.zeros(nl.cap_edges if static else max(nl.n_edges, 1), dtype=torch.int32, device=dev)
+    L.check(L.load().nn_nbr_edge_reverse(C.byref(nl.struct), rev.data_ptr(), _stream()), 'nn_nbr_edge_reverse')
+    row_ptr = torch.where(nl.status[L.ST_EDGE_OVERFLOW] != 0, torch.zeros_like(nl.row_ptr), nl.row_ptr)
+    seg_dst = Segments.from_csr(dst, N, row_ptr)
+    seg_src = Segments.from_csr(src, N, row_ptr, perm=rev)
     d = disp.norm(dim=1, keepdim=True)
     u = disp / d
     x = d / cutoff
@@ -446,7 +462,16 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     freq = emb.edge_embedding.embedding.frequencies
     rbf = RbfScale.apply(torch.ones_like(x), x, freq.detach().to(torch.float32).contiguous(), 0)
     rbf_pad = Fn.pad(rbf, (0, F - rbf.shape[1]))
-    a = Fn.embedding(z, emb.node_embedding.weight, padding_idx=0)
+    # nn.Embedding(119, F, padding_idx=0) (models/newtonnet.py:131,142) as a one-hot contraction through the same GEMM: its
+    # weight gradient is then X^T dY on the tensor cores (deterministic) instead of ATen's atomic embedding backward
+    # (3 x 104 us per step).  Exact: one-hot entries are 1.0 / 0.0 and B = B_hi + B_lo is summed exactly in fp32.
+    w_emb = emb.node_embedding.weight
+    if w_emb.shape[0] > F:
+        raise NotImplementedError('embedding tables with more than 128 rows')
+    keep = torch.ones(w_emb.shape[0], 1, dtype=torch.float32, device=dev)
+    keep[0] = 0.0                                            # padding_idx = 0: row 0 neither contributes nor receives a gradient
+    onehot = (z.unsqueeze(1) == torch.arange(F, device=dev).unsqueeze(0)).to(torch.float32)   # no host sync (graph capture)
+    a = Gemm.apply(onehot, Fn.pad(w_emb * keep, (0, 0, 0, F - w_emb.shape[0])))
     f = torch.zeros(N, 3 * F, dtype=torch.float32, device=dev)
     for layer in model.interaction_layers:
         n0, n2 = layer.message_nodepart[0], layer.message_nodepart[2]
