@@ -205,6 +205,10 @@ NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream);
 /* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo
  * parts, laid out as UMMA K-major 128B-swizzled blocks; `image` holds NN_B_IMAGE_FLOATS floats. */
 NN_API int nn_gemm128_prepare_b(const float* B, float* image, void* stream);
+/* the same for n matrices in one launch; src / image are HOST arrays of device pointers, transposed[i] != 0 takes src[i]^T
+ * as the operand (a weight in its other orientation: forward x W^T and reverse g W need both images of W). */
+NN_API int nn_gemm128_prepare_b_batch(const float* const* src, const int32_t* transposed, float* const* image, int32_t n,
+                                      void* stream);
 /* backend for nn_gemm128 and nn_eval: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 with A and B in shared memory,
  * 2 = tcgen05 3xTF32 with the A operand in tensor memory (TS mode). */
 NN_API int nn_set_gemm_backend(int backend);

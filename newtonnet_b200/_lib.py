@@ -95,6 +95,7 @@ SYMBOLS = {
     'nn_nbr_edge_index': (C.c_int, [C.POINTER(Nbr), _fp, C.c_int64, _fp]),
     'nn_gemm128': (C.c_int, [C.POINTER(GemmArgs), _fp]),
     'nn_gemm128_prepare_b': (C.c_int, [_fp, _fp, _fp]),
+    'nn_gemm128_prepare_b_batch': (C.c_int, [_fp, _fp, _fp, C.c_int32, _fp]),
     'nn_set_gemm_backend': (C.c_int, [C.c_int]),
     'nn_get_gemm_backend': (C.c_int, []),
     'nn_eval_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -286,6 +286,23 @@ __global__ void k_prepare_b(const float* __restrict__ B, float* __restrict__ img
     img[(NKB * BLK_BYTES + off) / 4] = x - hi;
 }
 
+// the same for up to 64 matrices in one launch (blockIdx.y = matrix); transposed[i] != 0: the operand is src^T, i.e.
+// B[k][n] = src[n][k] (a weight used in its other orientation) - no transposed copy has to be materialised
+struct PrepBatch { const float* src[64]; float* img[64]; int transposed[64]; };
+__global__ void k_prepare_b_batch(PrepBatch p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 128 * 128) return;
+    const float* B = p.src[blockIdx.y];
+    float* img = p.img[blockIdx.y];
+    const int n = t >> 7, k = t & 127;
+    const float x = p.transposed[blockIdx.y] ? B[(size_t)n * 128 + k] : B[(size_t)k * 128 + n];
+    const float hi = tf32_hi(x);
+    const int kb = k >> 5, chunk = (k & 31) >> 2, e = k & 3;
+    const uint32_t off = (uint32_t)kb * BLK_BYTES + swz_offset_bytes(n, chunk) + e * 4;
+    img[off / 4] = hi;
+    img[(NKB * BLK_BYTES + off) / 4] = x - hi;
+}
+
 int g_num_sms = 0;
 bool g_attr_set[4][5] = {};
 
@@ -313,6 +330,22 @@ extern "C" int nn_gemm128_prepare_b(const float* B, float* image, void* stream) 
     NN_REQUIRE(B && image, "null pointer");
     k_prepare_b<<<128 * 128 / 256, 256, 0, (cudaStream_t)stream>>>(B, image); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_gemm128_prepare_b");
+    return 0;
+}
+
+extern "C" int nn_gemm128_prepare_b_batch(const float* const* src, const int32_t* transposed, float* const* image, int32_t n,
+                                          void* stream) {
+    NN_REQUIRE(src && transposed && image && n >= 0, "null pointer");
+    for (int i0 = 0; i0 < n; i0 += 64) {
+        PrepBatch p;
+        const int m = n - i0 < 64 ? n - i0 : 64;
+        for (int i = 0; i < m; ++i) {
+            NN_REQUIRE(src[i0 + i] && image[i0 + i], "null matrix pointer");
+            p.src[i] = src[i0 + i]; p.img[i] = image[i0 + i]; p.transposed[i] = transposed[i0 + i];
+        }
+        k_prepare_b_batch<<<dim3(128 * 128 / 256, m), 256, 0, (cudaStream_t)stream>>>(p); NN_LAUNCHED(1);
+    }
+    NN_CHECK_LAUNCH("nn_gemm128_prepare_b_batch");
     return 0;
 }
 

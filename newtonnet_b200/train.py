@@ -37,31 +37,59 @@ def _stream():
 _image_cache = {}
 
 
-def _operand_image(B, Bc):
-    lib = L.load()
+def _image_key(B):
     base = B._base if B._base is not None else B
-    key = None
     if base.is_leaf and isinstance(base, torch.nn.Parameter):
-        key = (B.data_ptr(), base._version, tuple(B.shape), tuple(B.stride()))
+        return (B.data_ptr(), base._version, tuple(B.shape), tuple(B.stride()))
+    return None
+
+
+def prepare_weight_images(model):
+    """Both operand images (W and W^T) of every 128x128 weight of the model in ONE launch, registered in the step's
+    cache under the keys the GEMM calls of forward / backward / double backward will ask for.  Replaces ~58 single
+    prepare launches and as many transposed-copy kernels per training step."""
+    lib = L.load()
+    mats = [p for p in model.parameters() if p.dim() == 2 and tuple(p.shape) == (128, 128) and p.is_cuda
+            and p.dtype == torch.float32 and p.is_contiguous()]
+    if not mats:
+        return
+    n = 2 * len(mats)
+    imgs = torch.empty(n, L.NN_B_IMAGE_FLOATS, dtype=torch.float32, device=mats[0].device)
+    src = (C.c_void_p * n)(); img = (C.c_void_p * n)(); tr = (C.c_int32 * n)()
+    for i, p in enumerate(mats):
+        for t in (0, 1):                       # t = 0: operand B = W ([K,N] = W as stored); t = 1: operand B = W^T (view p.t())
+            k = 2 * i + t
+            src[k], img[k], tr[k] = p.data_ptr(), imgs[k].data_ptr(), t
+            _image_cache[_image_key(p.t() if t else p)] = imgs[k]
+    L.check(lib.nn_gemm128_prepare_b_batch(src, tr, img, n, _stream()), 'nn_gemm128_prepare_b_batch')
+
+
+def _operand_image(B):
+    """Operand image of B [128,128] (any strides): from the step's cache, else prepared now from a contiguous copy."""
+    key = _image_key(B)
+    if key is not None:
         img = _image_cache.get(key)
         if img is not None:
             return img
+    Bc = _c(B)
     img = torch.empty(L.NN_B_IMAGE_FLOATS, dtype=torch.float32, device=Bc.device)
-    L.check(lib.nn_gemm128_prepare_b(Bc.data_ptr(), img.data_ptr(), _stream()), 'nn_gemm128_prepare_b')
+    L.check(L.load().nn_gemm128_prepare_b(Bc.data_ptr(), img.data_ptr(), _stream()), 'nn_gemm128_prepare_b')
     if key is not None:
         _image_cache[key] = img
     return img
 
 
-def _gemm_raw(X, B, B_orig=None):
+def _gemm_raw(X, B):
     lib = L.load()
     M = X.shape[0]
     Y = torch.empty(M, 128, dtype=torch.float32, device=X.device)
     if M == 0:
         return Y
-    img = _operand_image(B if B_orig is None else B_orig, B)
+    img = _operand_image(B)
     a = L.GemmArgs()
-    a.X, a.B, a.B_img, a.Y, a.m = X.data_ptr(), B.data_ptr(), img.data_ptr(), Y.data_ptr(), M
+    # the row-major matrix itself is read by the SIMT back-end only; the tensor-core back-ends take the image
+    Bm = _c(B) if lib.nn_get_gemm_backend() == 0 else B
+    a.X, a.B, a.B_img, a.Y, a.m = X.data_ptr(), Bm.data_ptr(), img.data_ptr(), Y.data_ptr(), M
     L.check(lib.nn_gemm128(C.byref(a), _stream()), 'nn_gemm128')
     return Y
 
@@ -87,7 +115,7 @@ class Gemm(torch.autograd.Function):
         # save the inputs themselves: a contiguous copy made here would be cut off from the graph, and
         # the double backward needs d(dX)/dB through them
         ctx.save_for_backward(X, B)
-        return _gemm_raw(_c(X), _c(B), B)
+        return _gemm_raw(_c(X), B)
 
     @staticmethod
     def backward(ctx, dY):
@@ -437,6 +465,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     cutoff = model.cutoff
     N, F = pos.shape[0], L.NN_F
     _image_cache.clear()                                    # operand images live for one step
+    prepare_weight_images(model)
     if model.embedding_layers.requires_dr and pos.is_leaf and not pos.requires_grad:
         pos.requires_grad = True
     # ---- edges (reference order) from the cell-list kernel; image shifts are constants of the graph
