@@ -174,7 +174,15 @@ typedef struct {
     const int32_t* m_dev; int32_t m_dev_mul;   /* rows = m_dev[0] * m_dev_mul when m_dev != NULL */
     int32_t m;
     int32_t prologue, epilogue;
+    int32_t aux_tiled;              /* NN_EPI_MUL only: aux1 is stored tile-transposed (NN_TILED_INDEX), as the chained kernel writes it */
+    int32_t pad_;
 } nn_gemm_args;
+/* Tile-transposed ("row-owner") layout of an [M,128] fp32 tensor: tiles of 128 rows, inside a tile the 16-byte chunk c
+ * (0..31) of row r (0..127) lives at float offset ((tile * 32 + c) * 128 + r) * 4.  tcgen05.ld / st hand every lane one ROW
+ * of the accumulator, so in this layout the 32 lanes of a warp touch 512 contiguous bytes per instruction and the
+ * activation-derivative tensors silu'(q) that travel between the forward and the reverse MLP kernels need no
+ * shared-memory transpose on either side.  Buffers in this layout hold ceil(M / 128) * 128 rows. */
+#define NN_TILED_INDEX(row, col) ((((size_t)((row) >> 7) * 32 + ((col) >> 2)) * 128 + ((row) & 127)) * 4 + ((col) & 3))
 NN_API int nn_gemm128(const nn_gemm_args* a, void* stream);
 /* Two chained contractions in one kernel (a cluster of two CTAs, the intermediate tile travels through distributed
  * shared memory instead of HBM):  Y = out( mid(X . B1) . B2 ).  Every two-layer 128->128 MLP of the path and its
@@ -200,6 +208,8 @@ typedef struct {
      * in lockstep, so X is fetched from HBM once (the second read is an L2 hit): equiv_message1 and equiv_message2 of one
      * layer share their input (models/newtonnet.py:218,222). */
     const float* B1_img_b; const float* B2_img_b; float* aux_out_b; float* Y_b;
+    int32_t aux_tiled;              /* aux_out (mid = SILU_SAVE) / aux1 (mid = MUL) are in the tile-transposed layout (NN_TILED_INDEX) */
+    int32_t pad_;
 } nn_gemm_chain_args;
 NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream);
 /* Writes the tensor-core operand image of B ([128,128] row-major K x N): B^T split into tf32 hi / lo
@@ -400,7 +410,10 @@ NN_API int nn_ew_silu(int32_t mode, const float* x, const float* a, const float*
 /* ---- reverse-sweep operators as standalone entry points; nn_eval composes exactly these.
  * They replace the autograd replay of DerivativeProperty._save_grad (models/output.py:66-73) piece by piece. */
 /* Y = silu(X M1^T + b1) M2^T + b2; `mid` receives the pre-activation, or silu'(pre-activation) when save_dact != 0 (what
- * nn_mlp_bwd consumes).  m_dev != NULL: pair-level call, rows = m_dev[0] <= m.  One chained launch where it pays. */
+ * nn_mlp_bwd consumes).  m_dev != NULL: pair-level call, rows = m_dev[0] <= m.  One chained launch where it pays; then `mid`
+ * is written in the tile-transposed layout (NN_TILED_INDEX) and must hold ceil(m / 128) * 128 rows - nn_mlp_mid_tiled tells
+ * which, for the same (m, m_dev != NULL) that nn_mlp_fwd / nn_mlp_bwd are called with. */
+NN_API int nn_mlp_mid_tiled(int32_t m, int32_t has_m_dev);
 NN_API int nn_mlp_fwd(const float* X, const nn_mat* M1, const float* b1, float* mid, const nn_mat* M2, const float* b2, float* Y,
                       int32_t m, const int32_t* m_dev, int32_t save_dact, void* stream);
 /* Y (+)= ((G M2) * dact) M1: the transpose of nn_mlp_fwd with respect to X.  `tmp` [m,128] may alias G. */

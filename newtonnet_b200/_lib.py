@@ -55,13 +55,14 @@ class Nbr(C.Structure):
 class GemmArgs(C.Structure):
     _fields_ = [('X', _fp), ('B', _fp), ('Y', _fp), ('B_img', _fp), ('bias', _fp), ('aux1', _fp), ('aux2', _fp), ('aux3', _fp), ('aux_out', _fp),
                 ('m_dev', _fp), ('m_dev_mul', C.c_int32), ('m', C.c_int32), ('prologue', C.c_int32),
-                ('epilogue', C.c_int32)]
+                ('epilogue', C.c_int32), ('aux_tiled', C.c_int32), ('pad_', C.c_int32)]
 
 
 class GemmChainArgs(C.Structure):
     _fields_ = [('X', _fp), ('B1_img', _fp), ('B2_img', _fp), ('bias1', _fp), ('bias2', _fp), ('aux1', _fp), ('aux2', _fp),
                 ('aux_out', _fp), ('Y', _fp), ('m_dev', _fp), ('m_dev_mul', C.c_int32), ('m', C.c_int32), ('mid', C.c_int32),
-                ('out', C.c_int32), ('B1_img_b', _fp), ('B2_img_b', _fp), ('aux_out_b', _fp), ('Y_b', _fp)]
+                ('out', C.c_int32), ('B1_img_b', _fp), ('B2_img_b', _fp), ('aux_out_b', _fp), ('Y_b', _fp), ('aux_tiled', C.c_int32),
+                ('pad_', C.c_int32)]
 
 
 class DDComm(C.Structure):
@@ -120,6 +121,7 @@ SYMBOLS = {
     'nn_ew_silu': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'nn_ew_rbf': (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_gemm128_chain': (C.c_int, [C.POINTER(GemmChainArgs), _fp]),
+    'nn_mlp_mid_tiled': (C.c_int, [C.c_int32, C.c_int32]),
     'nn_mlp_fwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, _fp, C.c_int32, _fp, C.c_int32, _fp]),
     'nn_mlp_bwd': (C.c_int, [_fp, C.POINTER(Mat), _fp, _fp, C.POINTER(Mat), _fp, C.c_int32, _fp, C.c_int32, _fp]),
     'nn_energy_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),

@@ -140,6 +140,22 @@ extern "C" int nn_set_gemm_backend(int backend) {
 }
 extern "C" int nn_get_gemm_backend(void) { return g_backend; }
 
+// The chained kernel keeps the activation-derivative tensor silu'(q) in the tile-transposed layout (NN_TILED_INDEX), and
+// the reverse MLP (chained or two launches) reads it there.  Writer and reader take the decision from the same predicate:
+// the chained kernel ran in the forward MLP <=> pair-level call (device row count) or a small node-level call.
+static bool tiled_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NN_AUX_TILED"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+static bool chain_runs_fwd(const int* m_dev, int m) { return g_backend == 2 && chain_enabled() && (m_dev || m <= chain_small_m()); }
+static bool aux_is_tiled(const int* m_dev, int m) { return tiled_enabled() && chain_runs_fwd(m_dev, m); }
+extern "C" int nn_mlp_mid_tiled(int32_t m, int32_t has_m_dev) {
+    static const int one = 1;
+    return aux_is_tiled(has_m_dev ? &one : nullptr, m) ? 1 : 0;
+}
+
+
 int nn_gemm128_launch(const nn_gemm_args& a, cudaStream_t s) {
     if (g_backend == 2) return nn_gemm128_ts_launch(a, s);
     return g_backend == 1 ? nn_gemm128_tc_launch(a, s) : nn_gemm128_simt_launch(a, s);
@@ -178,18 +194,20 @@ EvalWs carve_eval(void* base, size_t cap, int N, int B, int P, int L, bool bwd) 
     WsCarver c(base, cap);
     EvalWs w{};
     const size_t NF = (size_t)N * kF, PF = (size_t)P * kF;
+    // activation-derivative buffers may be held tile-transposed (NN_TILED_INDEX): whole tiles of 128 rows
+    const size_t NFt = (size_t)((N + 127) / 128 * 128) * kF, PFt = (size_t)((P + 127) / 128 * 128) * kF;
     for (int l = 0; l < L; ++l) {
         LayerBuf& b = w.layer[l];
-        b.pre = c.take<float>(NF); b.mn = c.take<float>(NF);
+        b.pre = c.take<float>(NFt); b.mn = c.take<float>(NF);
         b.f_out = c.take<float>(3 * NF); b.g = c.take<float>(3 * NF);
-        b.msg = c.take<float>(PF); b.q1 = c.take<float>(PF); b.e1 = c.take<float>(PF);
-        if (l > 0) { b.q2 = c.take<float>(PF); b.e2 = c.take<float>(PF); }
+        b.msg = c.take<float>(PF); b.q1 = c.take<float>(PFt); b.e1 = c.take<float>(PF);
+        if (l > 0) { b.q2 = c.take<float>(PFt); b.e2 = c.take<float>(PF); }
         b.ln_xhat = c.take<float>(NF); b.ln_rstd = c.take<float>(N);
     }
     w.a0 = c.take<float>(NF); w.a1 = c.take<float>(NF);
     w.rbf = c.take<float>((size_t)P * kNB); w.unit = c.take<float>((size_t)P * 3); w.dist = c.take<float>(P);
     w.drbf = bwd ? c.take<float>((size_t)P * kNB) : nullptr;
-    w.h1pre = c.take<float>(NF); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
+    w.h1pre = c.take<float>(NFt); w.h2pre = c.take<float>(NF); w.e_atom = c.take<float>(N);
     w.d1 = c.take<float>(NF); w.d2 = c.take<float>(NF);
     w.slices = nn_sum_slices(N, B);
     w.sum_part = c.take<double>((size_t)(B > 0 ? B : 1) * w.slices * 9);
@@ -206,6 +224,7 @@ EvalWs carve_eval(void* base, size_t cap, int N, int B, int P, int L, bool bwd) 
 
 struct Gemm {
     cudaStream_t s; int rc = 0;
+    bool aux_tiled_next = false;          // the next EPI_MUL launch reads its factor in the tile-transposed layout
     // fwd(M): x @ M^T -> B = M.wt ; bwd(M): g @ M -> B = M.w
     void fwd(const float* X, const nn_mat& M, float* Y, int m, int pro, int epi, const float* bias = nullptr,
              const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
@@ -217,11 +236,13 @@ struct Gemm {
     void mlp_fwd(const float* X, const nn_mat& M1, const float* b1, float* mid, const nn_mat& M2, const float* b2, float* Y,
                  int m, int pro_act, const int* m_dev = nullptr) {
         if (rc) return;
-        if (g_backend == 2 && chain_enabled() && (m_dev || m <= chain_small_m()) && M1.wt_img && M2.wt_img) {     // gemm_chain.cu
+        if (chain_runs_fwd(m_dev, m)) {     // gemm_chain.cu
+            if (!(M1.wt_img && M2.wt_img)) { nn_set_error("mlp_fwd: the chained kernel needs the operand images of both matrices"); rc = -1; return; }
             ProfScope ps(m_dev ? NN_STAGE_PAIR_GEMM : NN_STAGE_NODE_GEMM, s);
             nn_gemm_chain_args a{};
             a.X = X; a.B1_img = M1.wt_img; a.B2_img = M2.wt_img; a.bias1 = b1; a.bias2 = b2; a.aux_out = mid; a.Y = Y;
             a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_SILU_SAVE; a.out = NN_OUT_BIAS;
+            a.aux_tiled = aux_is_tiled(m_dev, m);
             rc = nn_gemm128_chain(&a, s);
             return;
         }
@@ -240,6 +261,7 @@ struct Gemm {
         a.X = X; a.B1_img = A1.wt_img; a.B2_img = A2.wt_img; a.aux_out = midA; a.Y = YA;
         a.B1_img_b = B1.wt_img; a.B2_img_b = B2.wt_img; a.aux_out_b = midB; a.Y_b = YB;
         a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_SILU_SAVE; a.out = NN_OUT_BIAS;
+        a.aux_tiled = aux_is_tiled(m_dev, m);
         rc = nn_gemm128_chain(&a, s);
         return true;
     }
@@ -252,10 +274,13 @@ struct Gemm {
             nn_gemm_chain_args a{};
             a.X = G; a.B1_img = M2.w_img; a.B2_img = M1.w_img; a.aux1 = dact; a.aux2 = accumulate ? Y : nullptr; a.Y = Y;
             a.m_dev = m_dev; a.m_dev_mul = 1; a.m = m; a.mid = NN_MID_MUL; a.out = accumulate ? NN_OUT_ADD : NN_OUT_BIAS;
+            a.aux_tiled = aux_is_tiled(m_dev, m);
             rc = nn_gemm128_chain(&a, s);
             return;
         }
+        aux_tiled_next = aux_is_tiled(m_dev, m);
         bwd(G, M2, tmp, m, NN_PRO_NONE, NN_EPI_MUL, nullptr, dact, nullptr, nullptr, m_dev);
+        aux_tiled_next = false;
         bwd(tmp, M1, Y, m, NN_PRO_NONE, accumulate ? NN_EPI_ADD : NN_EPI_BIAS, nullptr, accumulate ? Y : nullptr, nullptr, nullptr, m_dev);
     }
     void run(const float* X, const float* B, const float* B_img, float* Y, int m, int pro, int epi,
@@ -268,6 +293,7 @@ struct Gemm {
         if (pro == NN_PRO_SILU_SAVE) a.aux_out = const_cast<float*>(X);
         a.X = X; a.B = B; a.B_img = B_img; a.Y = Y; a.bias = bias; a.aux1 = aux1; a.aux2 = aux2; a.aux3 = aux3;
         a.m_dev = m_dev; a.m_dev_mul = mul; a.m = m; a.prologue = pro; a.epilogue = epi;
+        a.aux_tiled = (epi == NN_EPI_MUL && aux_tiled_next) ? 1 : 0;
         rc = nn_gemm128_launch(a, s);
     }
 };

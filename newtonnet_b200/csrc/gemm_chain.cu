@@ -38,7 +38,19 @@ constexpr int PDEPTH = 2;
 constexpr uint32_t SMEM_BYTES = 1024 + B_BYTES + (8 * PDEPTH + 8) * STG_BYTES + BAR_BYTES;
 constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
 constexpr int MMA_WARP = PRODUCER_WARPS + EPI_WARPS;
-constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 1);
+// Register files are allocated in groups of 4 warps, so the 17th (MMA) warp is charged as a whole warpgroup: launch with
+// 20 warps (3 idle ones complete that warpgroup) at 96 registers and rebalance with setmaxnreg - the MMA warpgroup and
+// the producers hand registers to the epilogue warps, whose v[32] + factor prefetch + staging values spilled 120-150
+// bytes per thread at 96 registers (local-memory traffic on the L1TEX pipe that already limits the kernel).  ptxas -v:
+// (80, 128, 64) compiles every variant with 0-20 bytes of spill stores; the MMA-issuing code needs ~64 (descriptors).
+// 256 R_prod + 256 R_epi + 128 R_mma <= 640 * 96.
+#ifndef NN_CHAIN_REGS_PROD
+#define NN_CHAIN_REGS_PROD 80
+#define NN_CHAIN_REGS_EPI 128
+#endif
+constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 4);
+constexpr int REGS_PROD = NN_CHAIN_REGS_PROD, REGS_EPI = NN_CHAIN_REGS_EPI, REGS_MMA = 64;
+static_assert(256 * REGS_PROD + 256 * REGS_EPI + 128 * REGS_MMA <= 640 * 96, "register budget");
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t A_COL0 = 256;
 
@@ -179,7 +191,82 @@ __device__ __forceinline__ void epilogue_role(const nn_gemm_chain_args& a, const
     }
 }
 
-template <int MID, int OUT>
+// Rank-0 epilogue for the tile-transposed layout of the activation-derivative tensor (a.aux_tiled): everything happens in
+// the row-owner layout tcgen05.ld delivers - lane = row.  silu'(q) is written (MID_SILU_SAVE) or read (MID_MUL) as 512
+// contiguous bytes per warp instruction (NN_TILED_INDEX), and the tile for rank 1 is sent from the same registers, so this
+// rank needs NO shared-memory transpose at all (the two-pass staging of the row-major variant was half of the LSU
+// shared-memory traffic of the rank that limits the pair, profiles/r1c_chain_summary.txt).
+template <int MID>
+__device__ __forceinline__ void epilogue_rank0_tiled(const nn_gemm_chain_args& a, const ChainCtx& x) {
+    const uint32_t sPst = x.sPst, tmem_base = x.tmem_base;
+    const uint32_t bar_t_full = x.bar_t_full, bar_t_empty = x.bar_t_empty, bar_ring_full = x.bar_ring_full,
+                   bar_ring_empty = x.bar_ring_empty;
+    const int warp = x.warp, lane = x.lane, cid = x.cid, ncl = x.ncl, M = x.M, my_tiles = x.my_tiles;
+    const int q = warp & 3, ew = warp - PRODUCER_WARPS, half = ew >> 2;
+    const int rt = q * 32 + lane;                                   // row inside the tile
+    const uint32_t ring_remote = map_to_rank(sPst + (half * 4 + q) * PDEPTH * STG_BYTES, 1);
+    const float* bias = a.bias1;
+    auto tiled = [&](const float* base_, int tile, int chunk) { return base_ + (((size_t)tile * 32 + chunk) * 128 + rt) * 4; };
+    float4 ax[8];
+    auto prefetch = [&](int tile, int c0) {
+        if (MID != MID_MUL) return;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ax[j] = ld4(tiled(a.aux1, tile, (c0 >> 2) + j));     // padded rows are allocated: always readable
+    };
+    if (x.has_work) prefetch(cid, half * 64);
+    uint32_t it = 0;
+    for (int t = 0; t < my_tiles; ++t, ++it) {
+        const int tile = cid + t * ncl;
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        const bool live = tile * TM + rt < M;
+        mbar_wait(bar_t_full + 8 * buf, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int c0 = half * 64 + c * 32;
+            const int kb = 2 * half + c, slot = q * 4 + kb;
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
+            if (c == 1) {
+                tc_fence_before();
+                mbar_arrive(bar_t_empty + 8 * buf);
+            }
+            float4 cur[8];
+            if (MID == MID_MUL) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cur[j] = ax[j];
+                if (c == 0) prefetch(tile, c0 + 32);
+                else if (t + 1 < my_tiles) prefetch(tile + ncl, half * 64);
+            }
+            const uint32_t full_remote = map_to_rank(bar_ring_full + 8 * slot, 1);
+            mbar_wait_cluster(bar_ring_empty + 8 * slot, (t & 1) ^ 1);       // rank 1 has read tile t-1's block
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 acc = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                float4 hmid;
+                if (MID == MID_SILU_SAVE) {
+                    const float4 xx = bias ? f4_add(acc, ld4(bias + c0 + 4 * j)) : acc;
+                    const float4 sg = make_float4(sigmoid_f(xx.x), sigmoid_f(xx.y), sigmoid_f(xx.z), sigmoid_f(xx.w));
+                    if (live)
+                        st4(const_cast<float*>(tiled(a.aux_out, tile, (c0 >> 2) + j)),
+                            make_float4(sg.x * fmaf(xx.x, 1.0f - sg.x, 1.0f), sg.y * fmaf(xx.y, 1.0f - sg.y, 1.0f),
+                                        sg.z * fmaf(xx.z, 1.0f - sg.z, 1.0f), sg.w * fmaf(xx.w, 1.0f - sg.w, 1.0f)));
+                    hmid = f4_mul(xx, sg);
+                } else {
+                    hmid = live ? f4_mul(acc, cur[j]) : f4_zero();
+                }
+                // ring block of the tiled variant is chunk-major ([chunk j][row]): 512 contiguous bytes per warp instruction on
+                // both sides (32 separate 16-byte pieces per instruction through the cluster network were measured slower)
+                st_async4(ring_remote + c * STG_BYTES + j * 512 + lane * 16, hmid, full_remote);
+            }
+        }
+    }
+}
+
+template <int MID, int OUT, bool TILED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm128_chain(nn_gemm_chain_args a_in) {
     // dual launch (Y_b != NULL): even clusters run chain A, odd clusters chain B over the same X tiles
     nn_gemm_chain_args a = a_in;
@@ -242,6 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
     ChainCtx ctx{base, sPst, sStg, tmem_base, bar_t_full, bar_t_empty, bar_ring_full, bar_ring_empty, smem_gen,
                  warp, lane, cid, ncl, M, my_tiles, has_work};
     if (warp < PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
         // ===================== producers: rows -> hi/lo split -> TMEM =====================
         const int q = warp & 3, h = warp >> 2;
         const int r4 = lane >> 3, c8 = lane & 7;
@@ -289,7 +377,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int ch = hf * 4 + j;
-                    const float4 x = *reinterpret_cast<const float4*>(blk + lane * 128 + ((ch ^ (lane & 7)) << 4));
+                    const float4 x = (TILED && rank == 1) ? *reinterpret_cast<const float4*>(blk + ch * 512 + lane * 16)
+                                                          : *reinterpret_cast<const float4*>(blk + lane * 128 + ((ch ^ (lane & 7)) << 4));
                     const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     hi[4 * j] = __float_as_uint(hh.x); hi[4 * j + 1] = __float_as_uint(hh.y);
                     hi[4 * j + 2] = __float_as_uint(hh.z); hi[4 * j + 3] = __float_as_uint(hh.w);
@@ -318,9 +407,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
             }
         }
         if (rank == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == MMA_WARP) {
-        if (lane == 0) mbar_wait(bar_b_full, 0);
-        if (lane == 0 && has_work) {
+    } else if (warp >= MMA_WARP) {                    // the MMA warp and three idle warps that complete its warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+        if (warp == MMA_WARP && lane == 0) mbar_wait(bar_b_full, 0);
+        if (warp == MMA_WARP && lane == 0 && has_work) {
             uint32_t it = 0;
             for (int t = 0; t < my_tiles; ++t, ++it) {
                 const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
@@ -346,8 +436,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
         }
         __syncwarp();
     } else {
-        if (rank == 0) epilogue_role<MID, OUT, 0>(a, ctx);
-        else epilogue_role<MID, OUT, 1>(a, ctx);
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        if (rank == 0) {
+            if (TILED) epilogue_rank0_tiled<MID>(a, ctx);
+            else epilogue_role<MID, OUT, 0>(a, ctx);
+        } else epilogue_role<MID, OUT, 1>(a, ctx);
     }
     tc_fence_before();
     cluster_sync_all();                               // no CTA leaves while its peer may still touch its shared memory
@@ -358,14 +451,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gemm12
 }
 
 int g_pairs = 0;
-bool g_attr_set[2][2] = {};
+bool g_attr_set[2][2][2] = {};
 
-template <int MID, int OUT>
+template <int MID, int OUT, bool TILED>
 int launch(const nn_gemm_chain_args& a, cudaStream_t s) {
-    if (!g_attr_set[MID][OUT]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm128_chain<MID, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (!g_attr_set[MID][OUT][TILED]) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm128_chain<MID, OUT, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { nn_set_error("nn_gemm128_chain: cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
-        g_attr_set[MID][OUT] = true;
+        g_attr_set[MID][OUT][TILED] = true;
     }
     if (g_pairs == 0) {
         int dev = 0, sms = 0; cudaGetDevice(&dev);
@@ -379,7 +472,7 @@ int launch(const nn_gemm_chain_args& a, cudaStream_t s) {
         if (clusters < 2) clusters = 2;
     }
     NN_LAUNCHED(1);
-    return launch_pdl(k_gemm128_chain<MID, OUT>, 2 * clusters, THREADS, SMEM_BYTES, s, a);
+    return launch_pdl(k_gemm128_chain<MID, OUT, TILED>, 2 * clusters, THREADS, SMEM_BYTES, s, a);
 }
 
 }  // namespace
@@ -396,8 +489,13 @@ extern "C" NN_API int nn_gemm128_chain(const nn_gemm_chain_args* a, void* stream
     if (a->m <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (a->mid == MID_SILU_SAVE) rc = a->out == OUT_BIAS ? launch<MID_SILU_SAVE, OUT_BIAS>(*a, s) : launch<MID_SILU_SAVE, OUT_ADD>(*a, s);
-    else rc = a->out == OUT_BIAS ? launch<MID_MUL, OUT_BIAS>(*a, s) : launch<MID_MUL, OUT_ADD>(*a, s);
+    if (a->aux_tiled) {
+        if (a->mid == MID_SILU_SAVE) rc = a->out == OUT_BIAS ? launch<MID_SILU_SAVE, OUT_BIAS, true>(*a, s) : launch<MID_SILU_SAVE, OUT_ADD, true>(*a, s);
+        else rc = a->out == OUT_BIAS ? launch<MID_MUL, OUT_BIAS, true>(*a, s) : launch<MID_MUL, OUT_ADD, true>(*a, s);
+    } else {
+        if (a->mid == MID_SILU_SAVE) rc = a->out == OUT_BIAS ? launch<MID_SILU_SAVE, OUT_BIAS, false>(*a, s) : launch<MID_SILU_SAVE, OUT_ADD, false>(*a, s);
+        else rc = a->out == OUT_BIAS ? launch<MID_MUL, OUT_BIAS, false>(*a, s) : launch<MID_MUL, OUT_ADD, false>(*a, s);
+    }
     if (rc) return rc;
     NN_CHECK_LAUNCH("nn_gemm128_chain");
     return 0;

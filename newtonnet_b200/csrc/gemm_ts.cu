@@ -25,7 +25,16 @@ constexpr int PDEPTH = 2;                     // cp.async staging buffers per pr
 constexpr uint32_t SMEM_BYTES = 1024 + B_BYTES + (8 * PDEPTH + 8) * STG_BYTES + BAR_BYTES;   // B image + producer / epilogue staging
 constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
 constexpr int MMA_WARP = PRODUCER_WARPS + EPI_WARPS;
-constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 1);
+// 20 warps (the MMA warp + 3 idle warps complete a warpgroup: register files are allocated per 4 warps) at 96 registers,
+// rebalanced with setmaxnreg - see gemm_chain.cu.  256 R_prod + 256 R_epi + 128 R_mma <= 640 * 96.
+#ifndef NN_TS_REGS_PROD
+#define NN_TS_REGS_PROD 80
+#define NN_TS_REGS_EPI 128
+#define NN_TS_REGS_MMA 64
+#endif
+constexpr int THREADS = 32 * (PRODUCER_WARPS + EPI_WARPS + 4);
+constexpr int REGS_PROD = NN_TS_REGS_PROD, REGS_EPI = NN_TS_REGS_EPI, REGS_MMA = NN_TS_REGS_MMA;
+static_assert(256 * REGS_PROD + 256 * REGS_EPI + 128 * REGS_MMA <= 640 * 96, "register budget");
 constexpr uint32_t TMEM_COLS = 512;           // 2 x 128 accumulator columns + 4 K blocks x 64 columns of A
 constexpr uint32_t A_COL0 = 256;
 
@@ -70,7 +79,7 @@ __device__ __forceinline__ float4 epilogue(const nn_gemm_args& a, float4 acc, in
     return acc;
 }
 
-template <int PRO, int EPI>
+template <int PRO, int EPI, bool TILED = false>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
@@ -116,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     const bool has_work = (int)blockIdx.x < n_tiles;
 
     if (warp < PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
         // ===================== producers: X rows -> transpose -> hi/lo split -> TMEM =====================
         // warp = (lane quarter q, K-block half h): rows [32q, 32q+32) of K blocks 2h and 2h+1 of every tile.
         // cp.async (LDGSTS) brings each 32 x 32 block into a swizzled staging buffer in the coalesced
@@ -184,10 +194,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
             else asm volatile("cp.async.commit_group;" ::: "memory");
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == MMA_WARP) {
-        // ===================== B load + MMA issue (one elected lane) =====================
-        if (lane == 0) mbar_wait(bar_b_full, 0);           // the image copy must have landed before the CTA may exit
-        if (lane == 0 && has_work) {
+    } else if (warp >= MMA_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+        // ===================== B load + MMA issue (one elected lane of warp 16; warps 17-19 idle) =====================
+        if (warp == MMA_WARP && lane == 0) mbar_wait(bar_b_full, 0);           // the image copy must have landed before the CTA may exit
+        if (warp == MMA_WARP && lane == 0 && has_work) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
         }
         __syncwarp();
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         // ===================== epilogue: TMEM -> registers -> smem transpose -> global =====================
         // 8 warps: TMEM lane quarter q = warp % 4 (hardware restriction), column half = (warp - 8) / 4.
         // tcgen05.ld hands every lane one accumulator ROW; storing that straight to global memory would
@@ -226,8 +238,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
         uint8_t* stg = smem_gen + (sStg - base) + ew * STG_BYTES;
         uint32_t it = 0;
         float4 ax[8];
+        // EPI_MUL with a tile-transposed factor (a.aux_tiled, written by the chained kernel): the factor is read and applied
+        // in the row-owner layout, straight after tcgen05.ld (lane = row: 512 contiguous bytes per warp instruction)
+        constexpr bool tiled = TILED;
+        const int rt = q * 32 + lane;
         auto prefetch = [&](int tile, int c0) {
             if (!kAux1) return;
+            if (tiled) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ax[j] = ld4(a.aux1 + (((size_t)tile * 32 + (c0 >> 2) + j) * 128 + rt) * 4);
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int grow = tile * TM + q * 32 + k * 4 + r4;
@@ -250,6 +271,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
                     tc_fence_before();
                     mbar_arrive(bar_t_empty + 8 * buf);
                 }
+                if (tiled) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) * ax[j].x);
+                        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) * ax[j].y);
+                        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) * ax[j].z);
+                        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) * ax[j].w);
+                    }
+                    if (c == 0) prefetch(tile, c0 + 32);
+                    else if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, half * 64);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)         // row = lane, 16-byte chunk j -> physical chunk j ^ (lane & 7)
                     *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
@@ -257,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 __syncwarp();
                 float4 cur[8];
-                if (kAux1) {
+                if (kAux1 && !tiled) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) cur[k] = ax[k];
                     if (c == 0) prefetch(tile, c0 + 32);
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
                         } else if (EPI == NN_EPI_ADD) {
                             acc = f4_add(acc, cur[k]);
                         } else if (EPI == NN_EPI_MUL) {
-                            acc = f4_mul(acc, cur[k]);
+                            if (!tiled) acc = f4_mul(acc, cur[k]);
                         } else {
                             acc = epilogue<EPI>(a, acc, grow, col);
                         }
@@ -296,14 +328,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[4][5] = {};
+bool g_attr_set[4][5][2] = {};
 
-template <int PRO, int EPI>
+template <int PRO, int EPI, bool TILED = false>
 int launch(const nn_gemm_args& a, cudaStream_t s) {
-    if (!g_attr_set[PRO][EPI]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm128_ts<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (!g_attr_set[PRO][EPI][TILED]) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm128_ts<PRO, EPI, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { nn_set_error("nn_gemm128(ts): cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
-        g_attr_set[PRO][EPI] = true;
+        g_attr_set[PRO][EPI][TILED] = true;
     }
     if (g_num_sms == 0) {
         int dev = 0; cudaGetDevice(&dev);
@@ -313,7 +345,7 @@ int launch(const nn_gemm_args& a, cudaStream_t s) {
     int tiles = nn_ceil_div(a.m, TM);
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
     NN_LAUNCHED(1);
-    return launch_pdl(k_gemm128_ts<PRO, EPI>, grid, THREADS, SMEM_BYTES, s, a);
+    return launch_pdl(k_gemm128_ts<PRO, EPI, TILED>, grid, THREADS, SMEM_BYTES, s, a);
 }
 
 }  // namespace
@@ -329,6 +361,7 @@ int nn_gemm128_ts_launch(const nn_gemm_args& a, cudaStream_t s) {
     NN_CASE(NN_PRO_NONE, NN_EPI_ADD)
     NN_CASE(NN_PRO_ROWSCALE3, NN_EPI_EQUIV_BWD)
     NN_CASE(NN_PRO_SILU_SAVE, NN_EPI_BIAS)
+    if (a.prologue == NN_PRO_NONE && a.epilogue == NN_EPI_MUL && a.aux_tiled) { rc = launch<NN_PRO_NONE, NN_EPI_MUL, true>(a, s); goto done; }
     NN_CASE(NN_PRO_NONE, NN_EPI_MUL)
 #undef NN_CASE
     nn_set_error("nn_gemm128: unsupported prologue/epilogue combination %d/%d", a.prologue, a.epilogue);

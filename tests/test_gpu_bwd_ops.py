@@ -52,7 +52,9 @@ def test_mlp_fwd_bwd(M, pair_level):
     keep = []
     M1, M2 = _mat(W1, keep), _mat(W2, keep)
     cnt = torch.tensor([M], dtype=torch.int32, device=DEV) if pair_level else None
-    mid, Y = torch.empty_like(X), torch.empty_like(X)
+    # `mid` is what nn_mlp_bwd consumes: whole tiles of 128 rows, tile-transposed when the chained kernel runs (NN_TILED_INDEX)
+    Mp = (M + 127) // 128 * 128
+    mid, Y = torch.zeros(Mp, 128, device=DEV), torch.empty_like(X)
     L.check(lib.nn_mlp_fwd(X.data_ptr(), C.byref(M1), b1.data_ptr(), mid.data_ptr(), C.byref(M2), b2.data_ptr(), Y.data_ptr(), M,
                            L.ptr(cnt), 1, s), 'nn_mlp_fwd')
     Xd = X.double().requires_grad_(True)
@@ -60,7 +62,10 @@ def test_mlp_fwd_bwd(M, pair_level):
     sig = torch.sigmoid(pre)
     want = (pre * sig) @ W2.double().t() + b2.double()
     torch.testing.assert_close(Y.double(), want.detach(), **TOL)
-    torch.testing.assert_close(mid.double(), (sig * (1 + pre * (1 - sig))).detach(), rtol=2e-5, atol=2e-6)
+    mid_rows = mid
+    if lib.nn_mlp_mid_tiled(M, int(pair_level)):
+        mid_rows = mid.view(Mp // 128, 32, 128, 4).permute(0, 2, 1, 3).reshape(Mp, 128)      # [tile][chunk][row][4] -> rows
+    torch.testing.assert_close(mid_rows[:M].double(), (sig * (1 + pre * (1 - sig))).detach(), rtol=2e-5, atol=2e-6)
     gX, = torch.autograd.grad(want, Xd, G.double())
     for accumulate in (0, 1):
         out = acc0.clone()

@@ -9,7 +9,21 @@ from test_gpu_parity import _gemm, dev
 pytestmark = pytest.mark.gpu
 
 
-def _chain(lib, X, B1, B2, mid, out, bias1=None, bias2=None, aux1=None, aux2=None, aux_out=None, Y=None, m_dev=None):
+def _tile(t):
+    """[M,128] rows -> the tile-transposed layout of include/newtonnet_b200.h (NN_TILED_INDEX), padded to whole tiles."""
+    M = t.shape[0]
+    Mp = (M + 127) // 128 * 128
+    p = torch.zeros(Mp, 128, dtype=t.dtype, device=t.device)
+    p[:M] = t
+    return p.view(Mp // 128, 128, 32, 4).permute(0, 2, 1, 3).contiguous().view(Mp, 128)
+
+
+def _untile(t, M):
+    Mp = t.shape[0]
+    return t.view(Mp // 128, 32, 128, 4).permute(0, 2, 1, 3).reshape(Mp, 128)[:M]
+
+
+def _chain(lib, X, B1, B2, mid, out, bias1=None, bias2=None, aux1=None, aux2=None, aux_out=None, Y=None, m_dev=None, tiled=0):
     from newtonnet_b200 import _lib as L
     s = torch.cuda.current_stream().cuda_stream
     imgs = []
@@ -22,6 +36,7 @@ def _chain(lib, X, B1, B2, mid, out, bias1=None, bias2=None, aux1=None, aux2=Non
     a.X, a.B1_img, a.B2_img, a.Y = X.data_ptr(), imgs[0].data_ptr(), imgs[1].data_ptr(), Y.data_ptr()
     a.bias1, a.bias2, a.aux1, a.aux2, a.aux_out = L.ptr(bias1), L.ptr(bias2), L.ptr(aux1), L.ptr(aux2), L.ptr(aux_out)
     a.m_dev, a.m_dev_mul, a.m, a.mid, a.out = L.ptr(m_dev), 1, X.shape[0], mid, out
+    a.aux_tiled = tiled
     L.check(lib.nn_gemm128_chain(C.byref(a), s), 'nn_gemm128_chain')
     torch.cuda.synchronize()
     return Y
@@ -105,3 +120,41 @@ def test_dual_chain_matches_two_single_chains(M):
         assert torch.equal(YA[:n], wantA[:n]) and torch.equal(YB[:n], wantB[:n])
         assert torch.equal(mA[:n], midA[:n]) and torch.equal(mB[:n], midB[:n])
         assert bool((YA[n:] == 3.0).all()) and bool((mB[n:] == 3.0).all())
+
+
+@pytest.mark.parametrize('M', [1, 127, 129, 4099, 74 * 128 * 3 + 77])
+def test_chain_tile_transposed_activation_derivative(M):
+    """aux_tiled: silu'(q) written / read in the tile-transposed layout (rank 0 without shared-memory transposes) - the same
+    bits as the row-major variant, for the forward chain, both reverse chains and the two-launch reverse (gemm_ts EPI_MUL)."""
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    lib.nn_set_gemm_backend(2)
+    g = torch.Generator(device='cpu').manual_seed(77 + M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev())
+    X, B1, B2, b1, b2, aux, acc0 = r(M, 128), r(128, 128) / 11.3, r(128, 128) / 11.3, r(128), r(128), r(M, 128), r(M, 128)
+    Mp = (M + 127) // 128 * 128
+    mid_rm = torch.empty_like(X)
+    want = _chain(lib, X, B1, B2, 0, 0, bias1=b1, bias2=b2, aux_out=mid_rm)
+    mid_t = torch.full((Mp, 128), 9.0, device=dev())
+    got = _chain(lib, X, B1, B2, 0, 0, bias1=b1, bias2=b2, aux_out=mid_t, tiled=1)
+    assert torch.equal(got, want) and torch.equal(_untile(mid_t, M), mid_rm)
+    aux_t = _tile(aux)
+    assert torch.equal(_chain(lib, X, B1, B2, 1, 0, aux1=aux_t, tiled=1), _chain(lib, X, B1, B2, 1, 0, aux1=aux))
+    a1, a2 = acc0.clone(), acc0.clone()
+    _chain(lib, X, B1, B2, 1, 1, aux1=aux_t, aux2=a1, Y=a1, tiled=1)
+    _chain(lib, X, B1, B2, 1, 1, aux1=aux, aux2=a2, Y=a2)
+    assert torch.equal(a1, a2)
+    # two-launch reverse: gemm_ts with the multiply epilogue reading the tiled factor
+    s = torch.cuda.current_stream().cuda_stream
+    img = torch.empty(L.NN_B_IMAGE_FLOATS, device=dev())
+    L.check(lib.nn_gemm128_prepare_b(B1.data_ptr(), img.data_ptr(), s), 'prepare_b')
+    outs = []
+    for factor, tiled in ((aux, 0), (aux_t, 1)):
+        Y = torch.empty_like(X)
+        a = L.GemmArgs()
+        a.X, a.B, a.B_img, a.Y, a.aux1, a.m = X.data_ptr(), B1.data_ptr(), img.data_ptr(), Y.data_ptr(), factor.data_ptr(), M
+        a.prologue, a.epilogue, a.aux_tiled = L.PRO_NONE, L.EPI_MUL, tiled
+        L.check(lib.nn_gemm128(C.byref(a), s), 'nn_gemm128')
+        torch.cuda.synchronize()
+        outs.append(Y)
+    assert torch.equal(outs[0], outs[1])
