@@ -175,7 +175,7 @@ typedef struct {
     int32_t m;
     int32_t prologue, epilogue;
     int32_t aux_tiled;              /* NN_EPI_MUL only: aux1 is stored tile-transposed (NN_TILED_INDEX), as the chained kernel writes it */
-    int32_t pad_;
+    int32_t xy_tiled;               /* bit 0: X is tile-transposed (NN_PRO_NONE + NN_EPI_BIAS); bit 1: Y is (NN_EPI_MUL with aux_tiled) */
 } nn_gemm_args;
 /* Tile-transposed ("row-owner") layout of an [M,128] fp32 tensor: tiles of 128 rows, inside a tile the 16-byte chunk c
  * (0..31) of row r (0..127) lives at float offset ((tile * 32 + c) * 128 + r) * 4.  tcgen05.ld / st hand every lane one ROW
@@ -416,7 +416,8 @@ NN_API int nn_ew_silu(int32_t mode, const float* x, const float* a, const float*
 NN_API int nn_mlp_mid_tiled(int32_t m, int32_t has_m_dev);
 NN_API int nn_mlp_fwd(const float* X, const nn_mat* M1, const float* b1, float* mid, const nn_mat* M2, const float* b2, float* Y,
                       int32_t m, const int32_t* m_dev, int32_t save_dact, void* stream);
-/* Y (+)= ((G M2) * dact) M1: the transpose of nn_mlp_fwd with respect to X.  `tmp` [m,128] may alias G. */
+/* Y (+)= ((G M2) * dact) M1: the transpose of nn_mlp_fwd with respect to X.  `tmp` may alias G; like `mid` it holds
+ * ceil(m / 128) * 128 rows (the intermediate may travel tile-transposed). */
 NN_API int nn_mlp_bwd(const float* G, const nn_mat* M2, const float* dact, float* tmp, const nn_mat* M1, float* Y, int32_t m,
                       const int32_t* m_dev, int32_t accumulate, void* stream);
 /* gh2[i,:] = scale[z_i] * w3 * silu'(h2pre[i,:]): d(sum of atomic energies)/d(second hidden layer), models/output.py:98-100 */

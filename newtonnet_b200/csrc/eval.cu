@@ -148,6 +148,13 @@ static bool tiled_enabled() {
     if (v < 0) { const char* e = getenv("NN_AUX_TILED"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
+static bool tmp_tiled_enabled() {
+    static int v = -1;
+    // measured (B200, pair-level contractions per step): c4 11.22 -> 11.52 ms, c2 7.49 -> 7.67 ms with the tiled intermediate:
+    // the register-held row loads of the second launch keep fewer bytes in flight than its cp.async staging - off by default
+    if (v < 0) { const char* e = getenv("NN_TMP_TILED"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 static bool chain_runs_fwd(const int* m_dev, int m) { return g_backend == 2 && chain_enabled() && (m_dev || m <= chain_small_m()); }
 static bool aux_is_tiled(const int* m_dev, int m) { return tiled_enabled() && chain_runs_fwd(m_dev, m); }
 extern "C" int nn_mlp_mid_tiled(int32_t m, int32_t has_m_dev) {
@@ -200,7 +207,7 @@ EvalWs carve_eval(void* base, size_t cap, int N, int B, int P, int L, bool bwd) 
         LayerBuf& b = w.layer[l];
         b.pre = c.take<float>(NFt); b.mn = c.take<float>(NF);
         b.f_out = c.take<float>(3 * NF); b.g = c.take<float>(3 * NF);
-        b.msg = c.take<float>(PF); b.q1 = c.take<float>(PFt); b.e1 = c.take<float>(PF);
+        b.msg = c.take<float>(PF); b.q1 = c.take<float>(PFt); b.e1 = c.take<float>(PFt);      // e1 also hosts the tiled intermediate of the reverse MLP
         if (l > 0) { b.q2 = c.take<float>(PFt); b.e2 = c.take<float>(PF); }
         b.ln_xhat = c.take<float>(NF); b.ln_rstd = c.take<float>(N);
     }
@@ -225,6 +232,7 @@ EvalWs carve_eval(void* base, size_t cap, int N, int B, int P, int L, bool bwd) 
 struct Gemm {
     cudaStream_t s; int rc = 0;
     bool aux_tiled_next = false;          // the next EPI_MUL launch reads its factor in the tile-transposed layout
+    int xy_tiled_next = 0;                // ... and its X (bit 0) / Y (bit 1) are tile-transposed
     // fwd(M): x @ M^T -> B = M.wt ; bwd(M): g @ M -> B = M.w
     void fwd(const float* X, const nn_mat& M, float* Y, int m, int pro, int epi, const float* bias = nullptr,
              const float* aux1 = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr,
@@ -278,10 +286,16 @@ struct Gemm {
             rc = nn_gemm128_chain(&a, s);
             return;
         }
+        // with a tile-transposed silu' the intermediate travels tile-transposed too (pair-level, non-accumulating): the first
+        // launch stores it straight from the tcgen05.ld registers, the second loads it straight into registers
         aux_tiled_next = aux_is_tiled(m_dev, m);
+        const bool tmp_tiled = aux_tiled_next && m_dev && !accumulate && tmp_tiled_enabled();
+        xy_tiled_next = tmp_tiled ? 2 : 0;
         bwd(G, M2, tmp, m, NN_PRO_NONE, NN_EPI_MUL, nullptr, dact, nullptr, nullptr, m_dev);
         aux_tiled_next = false;
+        xy_tiled_next = tmp_tiled ? 1 : 0;
         bwd(tmp, M1, Y, m, NN_PRO_NONE, accumulate ? NN_EPI_ADD : NN_EPI_BIAS, nullptr, accumulate ? Y : nullptr, nullptr, nullptr, m_dev);
+        xy_tiled_next = 0;
     }
     void run(const float* X, const float* B, const float* B_img, float* Y, int m, int pro, int epi,
              const float* bias = nullptr, const float* aux1 = nullptr, const float* aux2 = nullptr,
@@ -294,6 +308,7 @@ struct Gemm {
         a.X = X; a.B = B; a.B_img = B_img; a.Y = Y; a.bias = bias; a.aux1 = aux1; a.aux2 = aux2; a.aux3 = aux3;
         a.m_dev = m_dev; a.m_dev_mul = mul; a.m = m; a.prologue = pro; a.epilogue = epi;
         a.aux_tiled = (epi == NN_EPI_MUL && aux_tiled_next) ? 1 : 0;
+        a.xy_tiled = xy_tiled_next;
         rc = nn_gemm128_launch(a, s);
     }
 };

@@ -79,8 +79,14 @@ __device__ __forceinline__ float4 epilogue(const nn_gemm_args& a, float4 acc, in
     return acc;
 }
 
-template <int PRO, int EPI, bool TILED = false>
+// TILED: the EPI_MUL factor aux1 is tile-transposed; XT / YT: X / Y are tile-transposed (NN_TILED_INDEX) - a producer then
+// loads its rows straight into registers (no cp.async staging, no shared-memory read) and an epilogue stores straight from
+// the tcgen05.ld registers (no staging transpose): the intermediate of a two-launch reverse MLP travels in that layout.
+template <int PRO, int EPI, bool TILED = false, bool XT = false, bool YT = false>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
+    // register split per variant: a producer that holds its rows in registers needs more, its plain epilogue less
+    constexpr int kRegsProd = XT ? 120 : REGS_PROD, kRegsEpi = XT ? 88 : REGS_EPI;
+    static_assert(256 * kRegsProd + 256 * kRegsEpi + 128 * REGS_MMA <= 640 * 96, "register budget");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
     const uint32_t sB = base;                                             // [hi|lo][kb][16 KB]
@@ -124,7 +130,54 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
     const int n_tiles = (M + TM - 1) / TM;
     const bool has_work = (int)blockIdx.x < n_tiles;
 
-    if (warp < PRODUCER_WARPS) {
+    if (XT && warp < PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+        // ===================== producers, tile-transposed X: rows -> registers -> hi/lo split -> TMEM =====================
+        const int q = warp & 3, h = warp >> 2;
+        const int rt = q * 32 + lane;
+        const int my_tiles = has_work ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int n_items = my_tiles * 2;                 // item w = (tile w >> 1, K block 2h + (w & 1))
+        float4 cur[8], nxt[8];
+        auto load = [&](int w, float4 (&dst)[8]) {
+            const int tile = (int)blockIdx.x + (w >> 1) * (int)gridDim.x, kb = 2 * h + (w & 1);
+            const bool ok = w < n_items && tile * TM + rt < M;      // rows beyond M read as zeros
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                dst[ch] = ok ? ld4(a.X + (((size_t)tile * 32 + kb * 8 + ch) * 128 + rt) * 4) : f4_zero();
+        };
+        load(0, cur);
+        for (int w = 0; w < n_items; ++w) {
+            const int t_local = w >> 1, kb = 2 * h + (w & 1);
+            load(w + 1, nxt);                                 // the next item's rows are in flight while this one is split
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + kb * 64;
+            bool waited = false;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x = cur[hf * 4 + j];
+                    const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    hi[4 * j] = __float_as_uint(hh.x); hi[4 * j + 1] = __float_as_uint(hh.y);
+                    hi[4 * j + 2] = __float_as_uint(hh.z); hi[4 * j + 3] = __float_as_uint(hh.w);
+                    lo[4 * j] = __float_as_uint(x.x - hh.x); lo[4 * j + 1] = __float_as_uint(x.y - hh.y);
+                    lo[4 * j + 2] = __float_as_uint(x.z - hh.z); lo[4 * j + 3] = __float_as_uint(x.w - hh.w);
+                }
+                if (!waited) {
+                    mbar_wait(bar_a_empty + 8 * kb, (t_local & 1) ^ 1);
+                    tc_fence_after();
+                    waited = true;
+                }
+                tmem_st16(taddr + hf * 16, hi);
+                tmem_st16(taddr + 32 + hf * 16, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * kb);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) cur[ch] = nxt[ch];
+        }
+    } else if (warp < PRODUCER_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
         // ===================== producers: X rows -> transpose -> hi/lo split -> TMEM =====================
         // warp = (lane quarter q, K-block half h): rows [32q, 32q+32) of K blocks 2h and 2h+1 of every tile.
@@ -224,7 +277,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
         }
         __syncwarp();
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        if (XT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         // ===================== epilogue: TMEM -> registers -> smem transpose -> global =====================
         // 8 warps: TMEM lane quarter q = warp % 4 (hardware restriction), column half = (warp - 8) / 4.
         // tcgen05.ld hands every lane one accumulator ROW; storing that straight to global memory would
@@ -282,6 +336,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
                     if (c == 0) prefetch(tile, c0 + 32);
                     else if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, half * 64);
                 }
+                if (YT) {                            // tile-transposed output: 512 contiguous bytes per warp instruction, no staging
+                    static_assert(!YT || (EPI == NN_EPI_MUL && TILED) || EPI == NN_EPI_BIAS, "tiled output: MUL (tiled factor) or plain");
+                    if (tile * TM + rt < M) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            if (EPI == NN_EPI_BIAS && a.bias) o = f4_add(o, ld4(a.bias + c0 + 4 * j));
+                            st4(a.Y + (((size_t)tile * 32 + (c0 >> 2) + j) * 128 + rt) * 4, o);
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)         // row = lane, 16-byte chunk j -> physical chunk j ^ (lane & 7)
                     *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
@@ -328,14 +395,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm128_ts(nn_gemm_args a) {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[4][5][2] = {};
+bool g_attr_set[4][5][2][2][2] = {};
 
-template <int PRO, int EPI, bool TILED = false>
+template <int PRO, int EPI, bool TILED = false, bool XT = false, bool YT = false>
 int launch(const nn_gemm_args& a, cudaStream_t s) {
-    if (!g_attr_set[PRO][EPI][TILED]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm128_ts<PRO, EPI, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (!g_attr_set[PRO][EPI][TILED][XT][YT]) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm128_ts<PRO, EPI, TILED, XT, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { nn_set_error("nn_gemm128(ts): cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
-        g_attr_set[PRO][EPI][TILED] = true;
+        g_attr_set[PRO][EPI][TILED][XT][YT] = true;
     }
     if (g_num_sms == 0) {
         int dev = 0; cudaGetDevice(&dev);
@@ -345,7 +412,7 @@ int launch(const nn_gemm_args& a, cudaStream_t s) {
     int tiles = nn_ceil_div(a.m, TM);
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
     NN_LAUNCHED(1);
-    return launch_pdl(k_gemm128_ts<PRO, EPI, TILED>, grid, THREADS, SMEM_BYTES, s, a);
+    return launch_pdl(k_gemm128_ts<PRO, EPI, TILED, XT, YT>, grid, THREADS, SMEM_BYTES, s, a);
 }
 
 }  // namespace
@@ -355,6 +422,14 @@ int nn_gemm128_ts_launch(const nn_gemm_args& a, cudaStream_t s) {
     NN_REQUIRE(a.B_img != nullptr, "tensor-core backend needs B_img (nn_gemm128_prepare_b)");
     int rc = -1;
 #define NN_CASE(P, E) if (a.prologue == P && a.epilogue == E) { rc = launch<P, E>(a, s); goto done; }
+    if (a.xy_tiled) {
+        // tile-transposed X (bit 0) / Y (bit 1): the two launches of a reverse MLP handing their intermediate over in that layout
+        if (a.prologue == NN_PRO_NONE && a.epilogue == NN_EPI_MUL && a.aux_tiled && a.xy_tiled == 2) { rc = launch<NN_PRO_NONE, NN_EPI_MUL, true, false, true>(a, s); goto done; }
+        if (a.prologue == NN_PRO_NONE && a.epilogue == NN_EPI_BIAS && a.xy_tiled == 1) { rc = launch<NN_PRO_NONE, NN_EPI_BIAS, false, true, false>(a, s); goto done; }
+        nn_set_error("nn_gemm128: unsupported tile-transposed combination (prologue %d, epilogue %d, aux_tiled %d, xy_tiled %d)",
+                     a.prologue, a.epilogue, a.aux_tiled, a.xy_tiled);
+        return -1;
+    }
     NN_CASE(NN_PRO_NONE, NN_EPI_BIAS)
     NN_CASE(NN_PRO_SILU, NN_EPI_BIAS)
     NN_CASE(NN_PRO_NONE, NN_EPI_DSILU)

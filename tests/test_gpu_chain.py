@@ -158,3 +158,37 @@ def test_chain_tile_transposed_activation_derivative(M):
         torch.cuda.synchronize()
         outs.append(Y)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('M', [1, 129, 4099, 148 * 128 * 2 + 5])
+def test_two_launch_reverse_with_tile_transposed_intermediate(M):
+    """(X B1) * aux -> tmp -> tmp B2 with aux AND tmp tile-transposed (first launch stores from the tcgen05.ld registers, second
+    loads its rows straight into registers): the same bits as the row-major pair of launches; in place (tmp aliases X)."""
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    lib.nn_set_gemm_backend(2)
+    g = torch.Generator(device='cpu').manual_seed(5 + M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev())
+    X, B1, B2, aux = r(M, 128), r(128, 128) / 11.3, r(128, 128) / 11.3, r(M, 128)
+    want = _gemm(lib, _gemm(lib, X, B1, epi=L.EPI_MUL, aux1=aux), B2)
+    s = torch.cuda.current_stream().cuda_stream
+    imgs = []
+    for B in (B1, B2):
+        img = torch.empty(L.NN_B_IMAGE_FLOATS, device=dev())
+        L.check(lib.nn_gemm128_prepare_b(B.data_ptr(), img.data_ptr(), s), 'prepare_b')
+        imgs.append(img)
+    Mp = (M + 127) // 128 * 128
+    buf = torch.zeros(Mp, 128, device=dev())
+    buf[:M] = X                                        # in place: the intermediate overwrites the input tile by tile
+    aux_t = _tile(aux)
+    a = L.GemmArgs()
+    a.X, a.B, a.B_img, a.Y, a.aux1, a.m = buf.data_ptr(), B1.data_ptr(), imgs[0].data_ptr(), buf.data_ptr(), aux_t.data_ptr(), M
+    a.prologue, a.epilogue, a.aux_tiled, a.xy_tiled = L.PRO_NONE, L.EPI_MUL, 1, 2
+    L.check(lib.nn_gemm128(C.byref(a), s), 'nn_gemm128(mul, y tiled)')
+    Y = torch.empty(M, 128, device=dev())
+    b = L.GemmArgs()
+    b.X, b.B, b.B_img, b.Y, b.m = buf.data_ptr(), B2.data_ptr(), imgs[1].data_ptr(), Y.data_ptr(), M
+    b.prologue, b.epilogue, b.xy_tiled = L.PRO_NONE, L.EPI_BIAS, 1
+    L.check(lib.nn_gemm128(C.byref(b), s), 'nn_gemm128(x tiled)')
+    torch.cuda.synchronize()
+    assert torch.equal(Y, want)
