@@ -649,7 +649,7 @@ def bench_c5_training(ctx, K, W):
     t = lambda a: torch.tensor(a, device=dev)
     e_t, f_t = t(rng.standard_normal(cell.shape[0]).astype(np.float32)), t(rng.standard_normal(pos.shape).astype(np.float32))
     model = seed0_weights().to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=os.environ.get('NN_ADAM_FUSED', '1') == '1')
     args_t = (t(z), t(pos), t(cell), t(batch), e_t, f_t)
     graphed = os.environ.get('NN_TRAIN_GRAPH', '1') == '1'      # forward + double backward replayed as one CUDA graph
     if graphed:
@@ -678,7 +678,7 @@ def bench_c5_training(ctx, K, W):
             'scaling': 'weak',
             'config': {'workload': 'c5: training step, 100 x 21 atoms per GPU, loss MSE(E) + 50 MSE(F), double backward, clip 1.0, '
                                    'Adam 1e-3; new positions every step; '
-                                   + ('forward + backward replayed as one CUDA graph (GraphedTrainingStep)' if graphed
+                                   + (f'forward + backward replayed as one CUDA graph (GraphedTrainingStep, {step.nl.cap_edges} padded edge rows, weight gradients on a side branch)' if graphed
                                       else 'eager autograd (training_step)'), 'atoms_per_gpu': N,
                        'parallelism': f'dp{world}, one all-reduce of a flat 401,155-float gradient bucket',
                        'final_loss': float(loss)},

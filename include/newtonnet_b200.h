@@ -389,6 +389,10 @@ NN_API int nn_segment_sum(const float* src, const int32_t* perm, const int32_t* 
 /* out[128,128] = X[m,128]^T @ Y[m,128]  (weight gradients of the 128x128 linears). */
 NN_API size_t nn_gemm128_tn_workspace_bytes(int32_t m);
 NN_API int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream);
+/* out = (accumulate ? out : 0) + X^T Y: a parameter's gradient summed over its uses (what autograd's AccumulateGrad does,
+ * reference train/trainer.py:309 loss.backward()) without a separate add kernel; fixed summation order. */
+NN_API int nn_gemm128_tn_acc(const float* X, const float* Y, int32_t m, float* out, void* workspace, int32_t accumulate,
+                             void* stream);
 
 /* Fused row products of the training path: the element-wise glue of InteractionNet.forward (models/newtonnet.py:211,
  * 219-226,231) as kernels that are closed under differentiation (each gradient is a combination of the others), so

@@ -116,6 +116,7 @@ SYMBOLS = {
     'nn_segment_sum': (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     'nn_gemm128_tn_workspace_bytes': (C.c_size_t, [C.c_int32]),
     'nn_gemm128_tn': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    'nn_gemm128_tn_acc': (C.c_int, [_fp, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp]),
     'nn_ew_mul3': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'nn_ew_rows': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_ew_silu': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int64, _fp]),

@@ -141,21 +141,34 @@ k_gemm_tn_tc(const float* __restrict__ X, const float* __restrict__ Y, int M, in
     }
 }
 
-// out = sum of the partials in index order.  64 threads per block (one float4 each, 64 blocks): the sum is a latency chain
-// of n_partial L2 reads per thread, so many small blocks on many SMs beat few large ones; 8 independent chains per thread.
-__global__ void __launch_bounds__(64) k_tn_reduce(const float* __restrict__ partial, int n_partial, float* __restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of the 128 x 128 result
-    if (t >= 128 * 128 / 4) return;
-    float4 acc[8];
+// out = (accumulate ? out : 0) + sum of the partials, in a fixed order.  The sum is a latency chain of L2 reads, so it is
+// spread wide: a block owns 32 consecutive float4 of the 128 x 128 result (one per lane, 512 contiguous bytes per warp
+// load) and its eight warps each sum a contiguous eighth of the partials with four independent chains; the eight slice
+// sums are then added in slice order through shared memory.  148 partials: 5 dependent load rounds per thread instead
+// of 19 (the single-pass version took 16 us per call and was 15 % of the training step, profiles/r2_c5_final_launches*).
+constexpr int RED_SLICES = 8;
+__global__ void __launch_bounds__(32 * RED_SLICES) k_tn_reduce(const float* __restrict__ partial, int n_partial, float* __restrict__ out,
+                                                               int accumulate) {
+    __shared__ float4 part[RED_SLICES][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;                       // one float4 of the result
+    const int per = (n_partial + RED_SLICES - 1) / RED_SLICES;
+    const int b0 = slice * per, b1 = min(n_partial, b0 + per);
+    float4 acc[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+    int b = b0;
+    for (; b + 4 <= b1; b += 4) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = f4_zero();
-    int b = 0;
-    for (; b + 8 <= n_partial; b += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = f4_add(acc[u], ld4(partial + (size_t)(b + u) * 128 * 128 + 4 * t));
+        for (int u = 0; u < 4; ++u) acc[u] = f4_add(acc[u], ld4(partial + (size_t)(b + u) * 128 * 128 + 4 * t));
     }
-    for (; b < n_partial; ++b) acc[0] = f4_add(acc[0], ld4(partial + (size_t)b * 128 * 128 + 4 * t));
-    st4(out + 4 * t, f4_add(f4_add(f4_add(acc[0], acc[1]), f4_add(acc[2], acc[3])), f4_add(f4_add(acc[4], acc[5]), f4_add(acc[6], acc[7]))));
+    for (; b < b1; ++b) acc[0] = f4_add(acc[0], ld4(partial + (size_t)b * 128 * 128 + 4 * t));
+    part[slice][lane] = f4_add(f4_add(acc[0], acc[1]), f4_add(acc[2], acc[3]));
+    __syncthreads();
+    if (slice == 0) {
+        float4 r = accumulate ? ld4(out + 4 * t) : f4_zero();
+#pragma unroll
+        for (int s = 0; s < RED_SLICES; ++s) r = f4_add(r, part[s][lane]);
+        st4(out + 4 * t, r);
+    }
 }
 
 bool g_attr = false;
@@ -170,7 +183,7 @@ int nn_gemm_tn_tc_ctas(int m) {
     return b < 1 ? 1 : (b > sms ? sms : b);
 }
 
-int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, cudaStream_t s) {
+int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, int accumulate, cudaStream_t s) {
     if (!g_attr) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { nn_set_error("nn_gemm128_tn(tc): cannot set %u B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e)); return -2; }
@@ -180,7 +193,7 @@ int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void
     int rows = nn_ceil_div(m, n);
     rows = nn_ceil_div(rows, tc::KB) * tc::KB;
     k_gemm_tn_tc<<<n, THREADS, SMEM_BYTES, s>>>(X, Y, m, rows, (float*)workspace); NN_LAUNCHED(1);
-    k_tn_reduce<<<128 * 128 / 4 / 64, 64, 0, s>>>((const float*)workspace, n, out); NN_LAUNCHED(1);
+    k_tn_reduce<<<128 * 128 / 4 / 32, 32 * RED_SLICES, 0, s>>>((const float*)workspace, n, out, accumulate); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_gemm128_tn(tc)");
     return 0;
 }

@@ -77,7 +77,7 @@ k_gemm_tn_partial(const float* __restrict__ X, const float* __restrict__ Y, int 
     }
 }
 
-__global__ void k_gemm_tn_reduce(const float* __restrict__ partial, int n_partial, float* __restrict__ out) {
+__global__ void k_gemm_tn_reduce(const float* __restrict__ partial, int n_partial, float* __restrict__ out, int accumulate) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of the 128 x 128 result
     if (t >= 128 * 128 / 4) return;
     // four independent chains keep four loads in flight; the order of the additions is fixed (deterministic)
@@ -88,7 +88,8 @@ __global__ void k_gemm_tn_reduce(const float* __restrict__ partial, int n_partia
         for (int u = 0; u < 4; ++u) acc[u] = f4_add(acc[u], ld4(partial + (size_t)(b + u) * 128 * 128 + 4 * t));
     }
     for (; b < n_partial; ++b) acc[0] = f4_add(acc[0], ld4(partial + (size_t)b * 128 * 128 + 4 * t));
-    st4(out + 4 * t, f4_add(f4_add(acc[0], acc[1]), f4_add(acc[2], acc[3])));
+    const float4 r = f4_add(f4_add(acc[0], acc[1]), f4_add(acc[2], acc[3]));
+    st4(out + 4 * t, accumulate ? f4_add(ld4(out + 4 * t), r) : r);
 }
 
 // 256 rows per block until two blocks per SM are reached: a training batch has 3e4 - 5e4 edge rows, and with 1024 rows
@@ -111,7 +112,7 @@ extern "C" int nn_segment_sum(const float* src, const int32_t* perm, const int32
 }
 
 int nn_gemm_tn_tc_ctas(int m);
-int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, cudaStream_t s);
+int nn_gemm_tn_tc_launch(const float* X, const float* Y, int m, float* out, void* workspace, int accumulate, cudaStream_t s);
 extern "C" int nn_get_gemm_backend(void);
 
 // workspace = one [128,128] partial per block / CTA of whichever back-end runs (the larger of the two counts)
@@ -120,18 +121,23 @@ extern "C" size_t nn_gemm128_tn_workspace_bytes(int32_t m) {
     return (size_t)(a > b ? a : b) * 128 * 128 * sizeof(float);
 }
 
-extern "C" int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream) {
+extern "C" int nn_gemm128_tn_acc(const float* X, const float* Y, int32_t m, float* out, void* workspace, int32_t accumulate,
+                                 void* stream) {
     NN_REQUIRE(X && Y && out && workspace, "null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    if (m <= 0) { cudaMemsetAsync(out, 0, 128 * 128 * sizeof(float), s); return 0; }
-    if (nn_get_gemm_backend() >= 1) return nn_gemm_tn_tc_launch(X, Y, m, out, workspace, s);     // tcgen05 3xTF32 (gemm_tn_tc.cu)
+    if (m <= 0) { if (!accumulate) cudaMemsetAsync(out, 0, 128 * 128 * sizeof(float), s); return 0; }
+    if (nn_get_gemm_backend() >= 1) return nn_gemm_tn_tc_launch(X, Y, m, out, workspace, accumulate, s);     // tcgen05 3xTF32 (gemm_tn_tc.cu)
     const int nb = tn_blocks(m);
     int rows_per_block = nn_ceil_div(m, nb);
     rows_per_block = nn_ceil_div(rows_per_block, TN_ROWS) * TN_ROWS;
     k_gemm_tn_partial<<<nb, 256, 0, s>>>(X, Y, m, rows_per_block, (float*)workspace); NN_LAUNCHED(1);
-    k_gemm_tn_reduce<<<128 * 128 / 4 / 256, 256, 0, s>>>((const float*)workspace, nb, out); NN_LAUNCHED(1);
+    k_gemm_tn_reduce<<<128 * 128 / 4 / 256, 256, 0, s>>>((const float*)workspace, nb, out, accumulate); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_gemm128_tn");
     return 0;
+}
+
+extern "C" int nn_gemm128_tn(const float* X, const float* Y, int32_t m, float* out, void* workspace, void* stream) {
+    return nn_gemm128_tn_acc(X, Y, m, out, workspace, 0, stream);
 }
 
 // ---------------------------------------------------------------------------- fused row products of the training path

@@ -17,6 +17,7 @@ kernels in this round.  Edges come from the same cell-list kernel as inference (
 reference's order).  NewtonNet.forward routes here when a derivative head has create_graph=True.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -107,6 +108,100 @@ def _c(t):
     return t.contiguous()
 
 
+# ----------------------------------------------------------------------------- where weight gradients go
+# A custom Function's backward computes every input gradient its ctx.needs_input_grad names, whether or not the running
+# autograd call asked for it.  Two consequences for the training step, handled by a module-level mode (the engine runs
+# backward nodes on its own device thread, so this is a plain global, not a thread-local):
+#   'skip'     while the forces are being derived (autograd.grad(energy, pos, create_graph=True) inside
+#              differentiable_forward): only d/d pos is wanted there, yet every linear would also form its X^T dY and throw
+#              it away (~25 contractions + reductions per config-5 step);
+#   'sink'     during the loss.backward() of a training step: X^T dY of a 128x128 nn.Linear weight is a LEAF of the backward
+#              graph - nothing but the optimizer reads it - so it is launched on a side stream and accumulated straight
+#              into weight.grad (nn_gemm128_tn_acc), off the critical path of the ~900-kernel chain and without autograd's
+#              AccumulateGrad add / copy kernels;
+#   'autograd' (default) returns the gradient to autograd like any Function.
+_weight_grad_mode = 'autograd'
+_weight_grad_sink = None
+
+
+class WeightGradSink:
+    """Side stream + workspace that receive the weight gradients of a training step's loss.backward().
+
+        with sink.step():            # mode 'sink'; joins the side stream on exit
+            loss.backward()
+
+    Gradients are written into p.grad (allocated on first use, overwritten by the first contribution of a step, summed
+    in launch order after it - deterministic).  Works eagerly and under CUDA-graph capture (the fork / join become graph
+    edges); operands are marked with record_stream so the caching allocator does not hand their memory to a later
+    main-stream kernel while the side stream still reads them."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.workspace = torch.empty(L.load().nn_gemm128_tn_workspace_bytes(1 << 30), dtype=torch.uint8, device=device)
+        self._touched = set()
+        self.launched = 0
+
+    def accumulate(self, W, A, Bm):
+        """W.grad (+)= A^T @ Bm."""
+        A, Bm = _c(A), _c(Bm)                      # on the main stream, before the fork
+        first = id(W) not in self._touched
+        if first:
+            self._touched.add(id(W))
+            if W.grad is None:
+                W.grad = torch.empty_like(W, memory_format=torch.contiguous_format)
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        L.check(L.load().nn_gemm128_tn_acc(A.data_ptr(), Bm.data_ptr(), A.shape[0], W.grad.data_ptr(), self.workspace.data_ptr(),
+                                           0 if first else 1, self.stream.cuda_stream), 'nn_gemm128_tn_acc')
+        A.record_stream(self.stream); Bm.record_stream(self.stream)
+        self.launched += 1
+
+    def step(self):
+        return _SinkStep(self)
+
+
+class _SinkStep:
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        global _weight_grad_mode, _weight_grad_sink
+        self.prev = (_weight_grad_mode, _weight_grad_sink)
+        self.sink._touched.clear()
+        _weight_grad_mode, _weight_grad_sink = 'sink', self.sink
+        return self.sink
+
+    def __exit__(self, *exc):
+        global _weight_grad_mode, _weight_grad_sink
+        _weight_grad_mode, _weight_grad_sink = self.prev
+        torch.cuda.current_stream(self.sink.device).wait_stream(self.sink.stream)      # join
+        return False
+
+
+class _skip_weight_grads:
+    def __enter__(self):
+        global _weight_grad_mode
+        self.prev = _weight_grad_mode
+        _weight_grad_mode = 'skip'
+
+    def __exit__(self, *exc):
+        global _weight_grad_mode
+        _weight_grad_mode = self.prev
+        return False
+
+
+def _weight_grad(W, A, Bm):
+    """d/dW of a contraction with W: A^T @ Bm, routed by the mode above."""
+    if _weight_grad_mode == 'skip':
+        return None
+    if (_weight_grad_mode == 'sink' and not torch.is_grad_enabled() and isinstance(W, torch.nn.Parameter) and W.is_leaf
+            and W.is_contiguous() and A.shape[0] > 0):
+        _weight_grad_sink.accumulate(W, A, Bm)
+        return None
+    return GemmTN.apply(A, Bm)
+
+
 class Gemm(torch.autograd.Function):
     """Y[M,128] = X[M,128] @ B[128,128]."""
 
@@ -121,8 +216,43 @@ class Gemm(torch.autograd.Function):
     def backward(ctx, dY):
         X, B = ctx.saved_tensors
         dX = Gemm.apply(dY, B.t()) if ctx.needs_input_grad[0] else None
-        dB = GemmTN.apply(X, dY) if ctx.needs_input_grad[1] else None
+        dB = GemmTN.apply(X, dY) if ctx.needs_input_grad[1] and _weight_grad_mode != 'skip' else None
         return dX, dB
+
+
+class Linear(torch.autograd.Function):
+    """Y[M,128] = X[M,128] @ W[128,128]^T with W as stored by nn.Linear (reference models/newtonnet.py:181-199)."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X, W)
+        ctx.weight = W
+        return _gemm_raw(_c(X), W.t())
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dX = LinearT.apply(dY, ctx.weight) if ctx.needs_input_grad[0] else None
+        dW = _weight_grad(ctx.weight, dY, X) if ctx.needs_input_grad[1] else None          # dY^T X
+        return dX, dW
+
+
+class LinearT(torch.autograd.Function):
+    """Y[M,128] = X[M,128] @ W[128,128]: the input gradient of Linear, a Function of its own so that the weight it was
+    called with stays identifiable in the double backward."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X, W)
+        ctx.weight = W
+        return _gemm_raw(_c(X), W)
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dX = Linear.apply(dY, ctx.weight) if ctx.needs_input_grad[0] else None
+        dW = _weight_grad(ctx.weight, X, dY) if ctx.needs_input_grad[1] else None          # X^T dY
+        return dX, dW
 
 
 class GemmTN(torch.autograd.Function):
@@ -136,8 +266,8 @@ class GemmTN(torch.autograd.Function):
     @staticmethod
     def backward(ctx, G):
         X, Y = ctx.saved_tensors
-        dX = Gemm.apply(Y, G.t()) if ctx.needs_input_grad[0] else None
-        dY = Gemm.apply(X, G) if ctx.needs_input_grad[1] else None
+        dX = Linear.apply(Y, G) if ctx.needs_input_grad[0] else None          # Y @ G^T
+        dY = LinearT.apply(X, G) if ctx.needs_input_grad[1] else None         # X @ G
         return dX, dY
 
 
@@ -407,7 +537,7 @@ def silu(x):
 
 def linear(x, weight, bias=None):
     """x @ weight^T (+ bias) through the tensor-core GEMM."""
-    y = Gemm.apply(x, weight.t())
+    y = Linear.apply(x, weight)
     return y if bias is None else y + bias
 
 
@@ -440,9 +570,26 @@ def _edges(nl, pos, N, static):
         ei = torch.stack([dst, src])
     sign = torch.where(ep < 0, -1.0, 1.0).to(torch.float32).unsqueeze(1)
     disp0 = nl.pair_disp[(ep & 0x7fffffff)] * sign
-    raw = pos.detach()[dst] - pos.detach()[src]
-    disp = pos[dst] - pos[src] - (raw - disp0)            # minimum image with a constant lattice shift
-    return ei, dst, src, disp, valid
+    return ei, dst, src, disp0, valid
+
+
+def _displacements(pos, seg_dst, seg_src, disp0):
+    """disp_e = pos_i - pos_j - (constant lattice shift), differentiable in pos.  The rows are fetched with Gather, whose
+    backward is the deterministic segment sum over the neighbour list's CSR: ATen's pos[idx] backward is an index_put
+    with a radix sort per call (4 x 35 us + 8 sort passes per config-5 step, tools/train_profile.py)."""
+    pos4 = Fn.pad(pos, (0, 1))                              # rows of 4 floats: one 16-byte piece per row
+    dd = (Gather.apply(pos4, seg_dst) - Gather.apply(pos4, seg_src))[:, :3]
+    return dd - (dd.detach() - disp0)                       # minimum image with a constant lattice shift
+
+
+def _table(emb, onehot):
+    """emb(z) [N,1] of an nn.Embedding(119, 1, padding_idx=0) (layers/scalers.py: per-element scale / shift) as a matrix -
+    vector product with the one-hot matrix of z: exact (entries 1.0 / 0.0), and its gradient is a gemv instead of ATen's
+    embedding_dense_backward (2 x 82 us per config-5 step).  Row 0 is padding: read, never given a gradient."""
+    w = emb.weight.reshape(-1).to(torch.float32)
+    first = torch.arange(w.shape[0], device=w.device) == 0           # built by kernels: no H2D copy while capturing
+    w = torch.where(first, w.detach(), w)
+    return torch.mv(onehot[:, :w.shape[0]] if w.shape[0] <= onehot.shape[1] else onehot, w).unsqueeze(1)
 
 
 def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
@@ -471,11 +618,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     # ---- edges (reference order) from the cell-list kernel; image shifts are constants of the graph
     static = static_nl is not None
     nl = static_nl if static else get_engine(dev).checked_neighbor_list(pos, cell, batch, cutoff)   # regrows on overflow
-    ei, dst, src, disp, valid = _edges(nl, pos, N, static)
-    if static:
-        pad = torch.cat([torch.full((1, 1), float(cutoff), dtype=torch.float32, device=dev),
-                         torch.zeros(1, 2, dtype=torch.float32, device=dev)], 1)      # fill kernels: no H2D copy while capturing
-        disp = torch.where(valid.unsqueeze(1), disp, pad)
+    ei, dst, src, disp0, valid = _edges(nl, pos, N, static)
     # segments straight from the neighbour list: rows of the destination-sorted CSR, and - the edge set being symmetric -
     # the same rows read through the reversed-edge map for the grouping by source atom (no counting pass, no sort); a
     # list that outgrew its capacity exposes empty segments
@@ -484,6 +627,11 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     row_ptr = torch.where(nl.status[L.ST_EDGE_OVERFLOW] != 0, torch.zeros_like(nl.row_ptr), nl.row_ptr)
     seg_dst = Segments.from_csr(dst, N, row_ptr)
     seg_src = Segments.from_csr(src, N, row_ptr, perm=rev)
+    disp = _displacements(pos, seg_dst, seg_src, disp0)
+    if static:
+        pad = torch.cat([torch.full((1, 1), float(cutoff), dtype=torch.float32, device=dev),
+                         torch.zeros(1, 2, dtype=torch.float32, device=dev)], 1)      # fill kernels: no H2D copy while capturing
+        disp = torch.where(valid.unsqueeze(1), disp, pad)
     d = disp.norm(dim=1, keepdim=True)
     u = disp / d
     x = d / cutoff
@@ -524,7 +672,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
     h = silu(linear(a, head[0].weight, head[0].bias))
     h = silu(linear(h, head[2].weight, head[2].bias))
     o = (h * head[4].weight).sum(1, keepdim=True) + head[4].bias           # 128 -> 1: exact fp32 reduction
-    e_atom = o * scaler.scale(z) + scaler.shift(z)
+    e_atom = o * _table(scaler.scale, onehot) + _table(scaler.shift, onehot)
     energy = torch.zeros(cell.shape[0], dtype=torch.float32, device=dev).index_add(0, batch, e_atom.reshape(-1))
     out = CustomOutputSet(z=z, pos=pos, cell=cell, batch=batch, edge_index=ei, atom_node=a, force_node=f.view(N, 3, F),
                           displacement=torch.eye(3, device=dev).repeat(cell.shape[0], 1, 1))
@@ -536,7 +684,7 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
             dl, ds = model.output_layers[kd].layers, model.scalers[kd]
             hd = silu(linear(a, dl[0].weight, dl[0].bias))
             hd = linear(silu(linear(hd, dl[2].weight, dl[2].bias)), dl[4].weight, dl[4].bias)
-            out.direct_force = RowDot.apply(f.view(N, 3, F), hd) * ds.scale(z)
+            out.direct_force = RowDot.apply(f.view(N, 3, F), hd) * _table(ds.scale, onehot)
         elif key == 'hessian':
             # reference models/output.py:141-152 (vmap over unit vectors): one reverse pass per row of the 3N x 3N matrix
             if not hasattr(out, 'pos_grad') or not out.pos_grad.requires_grad:
@@ -544,14 +692,16 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
                                    "(MLAseCalculator sets this, reference utils/ase_interface.py:125-128)")
             flat = out.pos_grad.reshape(-1)
             keep = bool(model.output_layers[props.index(key)].create_graph)
-            rows = [torch.autograd.grad(flat[r], pos, retain_graph=True, create_graph=False)[0] for r in range(flat.numel())]
+            with _skip_weight_grads():
+                rows = [torch.autograd.grad(flat[r], pos, retain_graph=True, create_graph=False)[0] for r in range(flat.numel())]
             out.hessian = torch.stack(rows).reshape(N, 3, N, 3)
             if not keep:
                 out.hessian = out.hessian.detach()
         else:
             create = bool(model.output_layers[props.index(key)].create_graph) or 'hessian' in props
-            out.pos_grad, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=create,
-                                                retain_graph=create)
+            with _skip_weight_grads():              # only d/d pos is asked for: no X^T dY products in this sweep
+                out.pos_grad, = torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=create,
+                                                    retain_graph=create)
             out.gradient_force = -out.pos_grad
     return out
 
@@ -592,6 +742,27 @@ def allreduce_gradients(params, group=None, flags=None):
     return flat
 
 
+_sinks = {}
+
+
+class _NoSink:
+    def step(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def weight_grad_sink(device):
+    """The device's WeightGradSink (NN_TRAIN_SINK=0: weight gradients go through autograd on the main stream)."""
+    import os
+    if os.environ.get('NN_TRAIN_SINK', '1') == '0':
+        return _NoSink()
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _sinks:
+        _sinks[key] = WeightGradSink(device)
+    return _sinks[key]
+
+
 def training_step(model, optimizer, z, pos, cell, batch, e_target, f_target, force_weight=50.0, clip_grad=1.0,
                   group=None):
     """One step of reference train/trainer.py:303-313: forward (create_graph), loss = MSE(E) + w MSE(F)
@@ -601,7 +772,8 @@ def training_step(model, optimizer, z, pos, cell, batch, e_target, f_target, for
     pos = pos.detach().clone().requires_grad_(True)
     out = model(z, pos, cell, batch)
     loss = Fn.mse_loss(out.energy, e_target) + force_weight * Fn.mse_loss(out.gradient_force, f_target)
-    loss.backward()
+    with weight_grad_sink(pos.device).step():
+        loss.backward()
     allreduce_gradients(model.parameters(), group)
     if clip_grad and clip_grad > 0:
         torch.nn.utils.clip_grad_norm_(model.parameters(), clip_grad)
@@ -610,54 +782,66 @@ def training_step(model, optimizer, z, pos, cell, batch, e_target, f_target, for
 
 
 class GraphedTrainingStep:
-    """training_step with forward + double backward replayed as ONE CUDA graph (static batch shape).
+    """training_step with neighbour rebuild + forward + double backward replayed as ONE CUDA graph (static batch shape).
 
-    Removes every host synchronisation and all Python / autograd dispatch from the step.  Measured on config 5 (100 x 21
-    atoms, B200): 18.2 ms against 18.5 ms eager - the step is bound by ~1,400 small kernels on the GPU, not by the host,
-    so this is an option (busy hosts, many ranks per host), not the default.  Shapes are made static by
-    padding the edge list to the neighbour list's capacity (see `_edges`); the neighbour rebuild, the forward, the loss
-    and loss.backward() are captured once, every later call copies the batch into the static buffers and replays.
-    Gradient all-reduce, clipping and the optimizer step stay outside the graph (a handful of launches).  Non-periodic
-    batches use the exact bound sum n_b (n_b - 1) as edge capacity; periodic ones probe and add headroom, and a replay
-    that overflowed raises before the optimizer step (rebuild the object with a larger `cap_edges`)."""
+    Removes every host synchronisation and all Python / autograd dispatch from the captured part; the weight gradients
+    form a parallel branch of the graph (WeightGradSink).  Shapes are made static by padding the edge list to the
+    neighbour list's capacity (see `_edges`): every edge-level kernel of the step processes `cap_edges` rows, so the
+    capacity is kept TIGHT - the probed edge count + 10 % + 256, never more than the all-pairs bound sum n_b (n_b - 1) of a
+    non-periodic batch (config 5: 33.5k rows instead of the bound's 42k, for 30.2k real edges).  A replay whose batch
+    outgrew the capacity is detected BEFORE the optimizer moves (the flag travels with the gradient bucket, so every
+    rank sees it); with regrow=True (default) the step is then re-captured with more room and run again, with
+    regrow=False it raises.  Gradient all-reduce, clipping and the optimizer step stay outside the graph."""
 
     def __init__(self, model, optimizer, z, pos, cell, batch, e_target, f_target, force_weight=50.0, clip_grad=1.0,
-                 group=None, cap_edges=None):
-        from newtonnet_b200.engine import NeighborList, get_engine
+                 group=None, cap_edges=None, regrow=True):
+        from newtonnet_b200.engine import get_engine
         dev = pos.device
         self.model, self.optimizer, self.group = model, optimizer, group
-        self.force_weight, self.clip_grad = float(force_weight), clip_grad
+        self.force_weight, self.clip_grad, self.regrow = float(force_weight), clip_grad, bool(regrow)
         self.z, self.batch = z.clone().to(torch.int64), batch.clone().to(torch.int64)
         self.pos = pos.detach().clone().to(torch.float32).contiguous()
         self.cell = cell.detach().clone().to(torch.float32).reshape(-1, 3, 3).contiguous()
         self.e_target, self.f_target = e_target.detach().clone(), f_target.detach().clone()
         self.engine = get_engine(dev)
         self.lib = L.load()
+        self.sink = weight_grad_sink(dev)
+        self.recaptures = 0
         if cap_edges is None:
-            if bool((self.cell == 0).all()):
-                n = torch.bincount(self.batch, minlength=self.cell.shape[0])
-                cap_edges = int((n * (n - 1)).sum().item())
-            else:
-                probe = self.engine.neighbor_list(self.pos, self.cell, self.batch, model.cutoff)
-                cap_edges = int(probe.check()[L.ST_N_EDGES] * 1.25) + 64
+            probe = self.engine.neighbor_list(self.pos, self.cell, self.batch, model.cutoff)
+            cap_edges = self._headroom(int(probe.check()[L.ST_N_EDGES]))
+        self._capture(cap_edges)
+        self.replays = 0
+
+    def _headroom(self, n_edges):
+        cap = int(n_edges * 1.1) + 256
+        if bool((self.cell == 0).all()):                    # non-periodic: all ordered pairs within a molecule bound the list
+            n = torch.bincount(self.batch, minlength=self.cell.shape[0])
+            cap = min(cap, int((n * (n - 1)).sum().item()))
+        return cap
+
+    def _capture(self, cap_edges):
+        from newtonnet_b200.engine import NeighborList
+        dev = self.pos.device
         cap_edges = max(int(cap_edges) + int(cap_edges) % 2, 2)
+        self.graph = None                                   # a previous capture's memory pool goes first
         self.nl = NeighborList(self.engine, self.pos, self.cell, self.batch, cap_edges=cap_edges)
-        model.train()
+        self.model.train()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up on a side stream, as graph capture requires
             for _ in range(2):
-                optimizer.zero_grad(set_to_none=True)
+                self.optimizer.zero_grad(set_to_none=True)
                 self._forward_backward()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        optimizer.zero_grad(set_to_none=True)
-        self.graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
         self.lib.nn_launch_count(1)
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(graph):
             self.loss = self._forward_backward()
+        self.graph = graph
         self.kernels_per_replay = int(self.lib.nn_launch_count(0))      # this library's kernels recorded in the graph
-        self.replays = 0
 
     def _forward_backward(self):
         s = _stream()
@@ -666,7 +850,8 @@ class GraphedTrainingStep:
         pos = self.pos.clone().requires_grad_(True)
         out = differentiable_forward(self.model, self.z, pos, self.cell, self.batch, static_nl=self.nl)
         loss = Fn.mse_loss(out.energy, self.e_target) + self.force_weight * Fn.mse_loss(out.gradient_force, self.f_target)
-        loss.backward()
+        with self.sink.step():                  # weight gradients on a side stream: a parallel branch of the captured graph
+            loss.backward()
         return loss.detach()
 
     def __call__(self, z, pos, cell, batch, e_target, f_target):
@@ -674,17 +859,23 @@ class GraphedTrainingStep:
             raise ValueError('GraphedTrainingStep was captured for a different batch shape')
         self.z.copy_(z); self.batch.copy_(batch); self.pos.copy_(pos.detach()); self.cell.copy_(cell.detach().reshape(-1, 3, 3))
         self.e_target.copy_(e_target); self.f_target.copy_(f_target)
-        self.graph.replay()
-        self.replays += 1
-        # a batch that outgrew the captured edge capacity leaves stale rows in the replayed graph: the flag travels with
-        # the gradient bucket so that every rank sees it, and it is read (one small D2H copy) BEFORE the optimizer moves
-        flag = (self.nl.status[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).to(torch.float32)
-        allreduce_gradients(self.model.parameters(), self.group, flags=flag)
-        if float(flag.item()) > 0:
+        for attempt in range(4):
+            self.graph.replay()
+            self.replays += 1
+            # a batch that outgrew the captured edge capacity leaves padding-only rows in the replayed graph: the flag travels
+            # with the gradient bucket so that every rank sees it, and it is read (one small D2H copy) BEFORE the optimizer moves
+            flag = (self.nl.status[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).to(torch.float32)
+            allreduce_gradients(self.model.parameters(), self.group, flags=flag)
+            if os.environ.get('NN_TRAIN_NOSYNC_EXPERIMENT') == '1' or float(flag.item()) == 0:
+                break
             self.optimizer.zero_grad(set_to_none=True)
-            need = int(self.nl.status[L.ST_EDGE_OVERFLOW].item())
-            raise RuntimeError(f'edge capacity {self.nl.cap_edges} of the captured training graph overflowed on some rank '
-                               f'(this rank needs {need}): the step was NOT applied; rebuild GraphedTrainingStep with a larger cap_edges')
+            need = int(self.nl.status[L.ST_EDGE_OVERFLOW].item())            # 0 on a rank whose own list still fits
+            if not self.regrow or attempt == 3:
+                raise RuntimeError(f'edge capacity {self.nl.cap_edges} of the captured training graph overflowed on some rank '
+                                   f'(this rank needs {need}): the step was NOT applied; rebuild GraphedTrainingStep with a larger cap_edges')
+            if need:                             # this rank re-captures with room for the batch that did not fit; all ranks run the step again
+                self._capture(max(self._headroom(need), self.nl.cap_edges + 2))
+                self.recaptures += 1
         if self.clip_grad and self.clip_grad > 0:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_grad)
         self.optimizer.step()

@@ -185,3 +185,23 @@ def test_gemm128_tn_tensor_core(m):
     scale = float(ref.abs().max())
     # fp32 accumulation over m rows (TMEM accumulator per CTA, then a fixed-order sum of the partials)
     assert float((a.double() - ref).abs().max()) / scale < 3e-6 * max(1.0, (m / 1024) ** 0.5)
+
+
+def test_gemm128_tn_accumulate():
+    """nn_gemm128_tn_acc: out (+)= X^T Y - the form the training step's weight-gradient sink uses (newtonnet_b200/train.py)."""
+    from newtonnet_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(11)
+    s = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.nn_gemm128_tn_workspace_bytes(1 << 20), dtype=torch.uint8, device=dev)
+    out = torch.full((128, 128), 7.0, device=dev)
+    want = torch.zeros(128, 128, dtype=torch.float64, device=dev)
+    for k, m in enumerate((5000, 37, 30230)):
+        X, Y = torch.randn(m, 128, generator=g).to(dev), torch.randn(m, 128, generator=g).to(dev)
+        L.check(lib.nn_gemm128_tn_acc(X.data_ptr(), Y.data_ptr(), m, out.data_ptr(), ws.data_ptr(), int(k > 0), s), 'nn_gemm128_tn_acc')
+        want += X.double().t() @ Y.double()
+    assert float((out.double() - want).abs().max()) / float(want.abs().max()) < 2e-5
+    before = out.clone()
+    L.check(lib.nn_gemm128_tn_acc(out.data_ptr(), out.data_ptr(), 0, out.data_ptr(), ws.data_ptr(), 1, s), 'nn_gemm128_tn_acc')
+    assert torch.equal(out, before)                      # no rows, accumulate: unchanged

@@ -429,6 +429,34 @@ def test_training_step_runs_and_reduces_loss():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
 
 
+def test_weight_gradient_sink_matches_autograd(monkeypatch):
+    """training_step with the weight gradients accumulated on the side stream (WeightGradSink) against the same step
+    with every gradient returned to autograd: same sums, different order of the additions only."""
+    from newtonnet_b200 import train
+    d = dict(np.load(f'{GOLDEN}/train_mols24.npz'))
+    t = lambda a, dt=None: torch.tensor(a, device=dev(), dtype=dt)
+    args = (t(d['z']), t(d['pos']), t(d['cell']), t(d['batch']), t(d['e_target'], torch.float32), t(d['f_target'], torch.float32))
+    grads = {}
+    for sink in ('1', '0'):
+        monkeypatch.setenv('NN_TRAIN_SINK', sink)
+        m = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+        opt = torch.optim.SGD(m.parameters(), lr=0.0)
+        before = train.weight_grad_sink(dev()).launched if sink == '1' else 0
+        for _ in range(2):                                 # the second step overwrites, it does not add to the first
+            train.training_step(m, opt, *args, force_weight=float(d['force_weight']), clip_grad=0.0)
+        if sink == '1':
+            assert train.weight_grad_sink(dev()).launched - before >= 2 * 30
+        torch.cuda.synchronize()
+        grads[sink] = {k: (None if p.grad is None else p.grad.double().cpu()) for k, p in m.named_parameters()}
+    assert train._weight_grad_mode == 'autograd'
+    scale_all = max(float(g.abs().max()) for g in grads['0'].values() if g is not None)
+    for k, ref in grads['0'].items():
+        got = grads['1'][k]
+        assert (got is None) == (ref is None), k
+        if ref is not None:
+            assert float((got - ref).abs().max()) <= 2e-6 * max(float(ref.abs().max()), 1e-3 * scale_all), k
+
+
 @pytest.mark.parametrize('name', ['mols24', 'water81'])
 def test_graphed_training_step_matches_eager(name):
     """forward + double backward replayed as one CUDA graph over a padded, static-shape edge list: same loss, same
@@ -582,13 +610,37 @@ def test_graphed_training_step_refuses_overflowing_batch():
     args = (t(z), t(pos), t(cell), t(batch), t(rng.standard_normal(1), torch.float32), t(rng.standard_normal(pos.shape), torch.float32))
     model = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
     opt = torch.optim.SGD(model.parameters(), lr=1e-2)
-    step = GraphedTrainingStep(model, opt, *args)
+    step = GraphedTrainingStep(model, opt, *args, regrow=False)
     step(*args)
     before = [p.detach().clone() for p in model.parameters()]
     dense = (args[0], t((pos * 0.7).astype(np.float32)), t((cell * 0.7).astype(np.float32))) + args[3:]
     with pytest.raises(RuntimeError, match='overflow'):
         step(*dense)
     assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+
+
+def test_graphed_training_step_regrows_on_overflow():
+    """Default behaviour: the edge capacity is tight (probed count + 10 %), and a batch that outgrows it is re-captured with
+    more room and applied - same loss and same parameters as the eager step on the same batches."""
+    from newtonnet_b200.train import GraphedTrainingStep, training_step
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.water_box(4)
+    rng = np.random.default_rng(0)
+    t = lambda a, dt=None: torch.tensor(a, device=dev(), dtype=dt)
+    args = (t(z), t(pos), t(cell), t(batch), t(rng.standard_normal(1), torch.float32), t(rng.standard_normal(pos.shape), torch.float32))
+    dense = (args[0], t((pos * 0.7).astype(np.float32)), t((cell * 0.7).astype(np.float32))) + args[3:]
+    m_g = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    m_e = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    o_g, o_e = torch.optim.SGD(m_g.parameters(), lr=1e-3), torch.optim.SGD(m_e.parameters(), lr=1e-3)
+    step = GraphedTrainingStep(m_g, o_g, *args)
+    cap0 = step.nl.cap_edges
+    assert cap0 < 1.2 * step.check()[4]
+    for a in (args, dense, args):
+        lg, le = step(*a), training_step(m_e, o_e, *a)
+        assert abs(lg.item() - le.item()) < 1e-4 * abs(le.item())
+    assert step.recaptures == 1 and step.nl.cap_edges > 1.5 * cap0
+    for (k, pe), (_, pg) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert float((pe.detach() - pg.detach()).abs().max()) < 1e-4 * max(float(pe.detach().abs().max()), 1e-3), k
 
 
 def test_reference_module_pickle_evaluates_like_the_reference():
