@@ -787,14 +787,20 @@ class GraphedTrainingStep:
     Removes every host synchronisation and all Python / autograd dispatch from the captured part; the weight gradients
     form a parallel branch of the graph (WeightGradSink).  Shapes are made static by padding the edge list to the
     neighbour list's capacity (see `_edges`): every edge-level kernel of the step processes `cap_edges` rows, so the
-    capacity is kept TIGHT - the probed edge count + 10 % + 256, never more than the all-pairs bound sum n_b (n_b - 1) of a
+    capacity is kept TIGHT - the probed edge count + 5 % + 256, never more than the all-pairs bound sum n_b (n_b - 1) of a
     non-periodic batch (config 5: 33.5k rows instead of the bound's 42k, for 30.2k real edges).  A replay whose batch
     outgrew the capacity is detected BEFORE the optimizer moves (the flag travels with the gradient bucket, so every
     rank sees it); with regrow=True (default) the step is then re-captured with more room and run again, with
-    regrow=False it raises.  Gradient all-reduce, clipping and the optimizer step stay outside the graph."""
+    regrow=False it raises.  Gradient all-reduce, clipping and the optimizer step stay outside the graph.
+
+    Host synchronisation: with an optimizer that can skip its step on a device flag (torch's fused Adam / AdamW / SGD,
+    `fused=True`) and deferred_check=True (default) a call never waits for the GPU: the overflow flag is handed to the
+    optimizer as its skip flag and read by the NEXT call (`settle()`), which re-captures and applies the skipped batch
+    before it goes on - parameters are the same as with the strict path; only the loss RETURNED by the overflowing call
+    is that of the empty padded graph.  Any other optimizer (or deferred_check=False) reads the flag every step."""
 
     def __init__(self, model, optimizer, z, pos, cell, batch, e_target, f_target, force_weight=50.0, clip_grad=1.0,
-                 group=None, cap_edges=None, regrow=True):
+                 group=None, cap_edges=None, regrow=True, deferred_check=True):
         from newtonnet_b200.engine import get_engine
         dev = pos.device
         self.model, self.optimizer, self.group = model, optimizer, group
@@ -807,6 +813,10 @@ class GraphedTrainingStep:
         self.lib = L.load()
         self.sink = weight_grad_sink(dev)
         self.recaptures = 0
+        self.deferred_check = bool(deferred_check)
+        self._pending = False
+        self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._flag_event = torch.cuda.Event()
         if cap_edges is None:
             probe = self.engine.neighbor_list(self.pos, self.cell, self.batch, model.cutoff)
             cap_edges = self._headroom(int(probe.check()[L.ST_N_EDGES]))
@@ -814,7 +824,7 @@ class GraphedTrainingStep:
         self.replays = 0
 
     def _headroom(self, n_edges):
-        cap = int(n_edges * 1.1) + 256
+        cap = int(n_edges * 1.05) + 256
         if bool((self.cell == 0).all()):                    # non-periodic: all ordered pairs within a molecule bound the list
             n = torch.bincount(self.batch, minlength=self.cell.shape[0])
             cap = min(cap, int((n * (n - 1)).sum().item()))
@@ -854,35 +864,82 @@ class GraphedTrainingStep:
             loss.backward()
         return loss.detach()
 
-    def __call__(self, z, pos, cell, batch, e_target, f_target):
-        if pos.shape != self.pos.shape or cell.reshape(-1, 3, 3).shape != self.cell.shape:
-            raise ValueError('GraphedTrainingStep was captured for a different batch shape')
-        self.z.copy_(z); self.batch.copy_(batch); self.pos.copy_(pos.detach()); self.cell.copy_(cell.detach().reshape(-1, 3, 3))
-        self.e_target.copy_(e_target); self.f_target.copy_(f_target)
+    def _device_skip(self):
+        return self.deferred_check and bool(getattr(self.optimizer, '_step_supports_amp_scaling', False))
+
+    def _apply(self, found_inf=None):
+        """Clip + optimizer step; found_inf (device flag, exactly 1.0 = skip) makes a fused optimizer leave the parameters
+        and its step count untouched without a host round trip (the mechanism torch.amp.GradScaler uses)."""
+        if self.clip_grad and self.clip_grad > 0:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_grad)
+        if found_inf is None:
+            self.optimizer.step()
+            return
+        self.optimizer.grad_scale, self.optimizer.found_inf = None, found_inf
+        try:
+            self.optimizer.step()
+        finally:
+            del self.optimizer.grad_scale, self.optimizer.found_inf
+
+    def _replay(self):
+        self.graph.replay()
+        self.replays += 1
+        # a batch that outgrew the captured edge capacity leaves padding-only rows in the replayed graph: the flag travels
+        # with the gradient bucket so that every rank sees it, and it is looked at BEFORE the optimizer moves
+        flag = (self.nl.status[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).to(torch.float32)
+        allreduce_gradients(self.model.parameters(), self.group, flags=flag)
+        return flag
+
+    def _run_strict(self, overflowed=False):
+        """Replay, read the overflow flag on the host (one small D2H copy per step), re-capture with more room while it is set,
+        then clip + step.  overflowed=True: the batch in the static buffers is already known not to fit."""
         for attempt in range(4):
-            self.graph.replay()
-            self.replays += 1
-            # a batch that outgrew the captured edge capacity leaves padding-only rows in the replayed graph: the flag travels
-            # with the gradient bucket so that every rank sees it, and it is read (one small D2H copy) BEFORE the optimizer moves
-            flag = (self.nl.status[L.ST_EDGE_OVERFLOW:L.ST_EDGE_OVERFLOW + 1] != 0).to(torch.float32)
-            allreduce_gradients(self.model.parameters(), self.group, flags=flag)
-            if os.environ.get('NN_TRAIN_NOSYNC_EXPERIMENT') == '1' or float(flag.item()) == 0:
-                break
-            self.optimizer.zero_grad(set_to_none=True)
+            if not overflowed:
+                if float(self._replay().item()) == 0:
+                    break
+            overflowed = False
             need = int(self.nl.status[L.ST_EDGE_OVERFLOW].item())            # 0 on a rank whose own list still fits
             if not self.regrow or attempt == 3:
+                self.optimizer.zero_grad(set_to_none=False)      # in place: the captured graph keeps writing these tensors
                 raise RuntimeError(f'edge capacity {self.nl.cap_edges} of the captured training graph overflowed on some rank '
                                    f'(this rank needs {need}): the step was NOT applied; rebuild GraphedTrainingStep with a larger cap_edges')
             if need:                             # this rank re-captures with room for the batch that did not fit; all ranks run the step again
                 self._capture(max(self._headroom(need), self.nl.cap_edges + 2))
                 self.recaptures += 1
-        if self.clip_grad and self.clip_grad > 0:
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_grad)
-        self.optimizer.step()
+        self._apply()
+
+    def settle(self):
+        """Deferred overflow check of the previous call (device-skip mode): waits for that call's flag; if its batch did
+        not fit, the optimizer skipped it on the device - the step is re-captured with more room and the batch, still in the
+        static buffers, is applied now.  Called at the start of every call and by check(); call it after the last step."""
+        if not self._pending:
+            return
+        self._pending = False
+        self._flag_event.synchronize()
+        if float(self._flag_host[0]) != 0:
+            self._run_strict(overflowed=True)
+
+    def __call__(self, z, pos, cell, batch, e_target, f_target):
+        if pos.shape != self.pos.shape or cell.reshape(-1, 3, 3).shape != self.cell.shape:
+            raise ValueError('GraphedTrainingStep was captured for a different batch shape')
+        self.settle()
+        self.z.copy_(z); self.batch.copy_(batch); self.pos.copy_(pos.detach()); self.cell.copy_(cell.detach().reshape(-1, 3, 3))
+        self.e_target.copy_(e_target); self.f_target.copy_(f_target)
+        if not self._device_skip():
+            self._run_strict()
+            return self.loss.clone()
+        # no host synchronisation in the step: the flag goes to pinned memory for the next call's settle(), and to the fused
+        # optimizer as its skip flag
+        flag = self._replay()
+        self._flag_host.copy_(flag, non_blocking=True)
+        self._flag_event.record()
+        self._pending = True
+        self._apply(found_inf=(flag > 0).to(torch.float32).reshape(()))      # 0-dim, as torch.amp.GradScaler passes it
         return self.loss.clone()
 
     def check(self):
         """Status words of the last replay (one host synchronisation): raises when the edge capacity overflowed."""
+        self.settle()
         st = self.nl.check()
         if st[L.ST_EDGE_OVERFLOW]:
             raise RuntimeError(f'edge capacity {self.nl.cap_edges} overflowed ({st[L.ST_EDGE_OVERFLOW]} needed)')

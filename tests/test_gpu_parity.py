@@ -620,7 +620,7 @@ def test_graphed_training_step_refuses_overflowing_batch():
 
 
 def test_graphed_training_step_regrows_on_overflow():
-    """Default behaviour: the edge capacity is tight (probed count + 10 %), and a batch that outgrows it is re-captured with
+    """Default behaviour: the edge capacity is tight (probed count + 5 %), and a batch that outgrows it is re-captured with
     more room and applied - same loss and same parameters as the eager step on the same batches."""
     from newtonnet_b200.train import GraphedTrainingStep, training_step
     from oracle import newtonnet_oracle as O
@@ -641,6 +641,37 @@ def test_graphed_training_step_regrows_on_overflow():
     assert step.recaptures == 1 and step.nl.cap_edges > 1.5 * cap0
     for (k, pe), (_, pg) in zip(m_e.named_parameters(), m_g.named_parameters()):
         assert float((pe.detach() - pg.detach()).abs().max()) < 1e-4 * max(float(pe.detach().abs().max()), 1e-3), k
+
+
+def test_graphed_training_step_deferred_overflow_check():
+    """Fused Adam: no host synchronisation per step - the overflowing batch is skipped ON THE DEVICE (optimizer skip flag),
+    found by the next call's settle(), re-captured and applied then.  Parameters follow the eager trajectory exactly."""
+    from newtonnet_b200.train import GraphedTrainingStep, training_step
+    from oracle import newtonnet_oracle as O
+    z, pos, cell, batch = O.water_box(4)
+    rng = np.random.default_rng(0)
+    t = lambda a, dt=None: torch.tensor(a, device=dev(), dtype=dt)
+    args = (t(z), t(pos), t(cell), t(batch), t(rng.standard_normal(1), torch.float32), t(rng.standard_normal(pos.shape), torch.float32))
+    dense = (args[0], t((pos * 0.7).astype(np.float32)), t((cell * 0.7).astype(np.float32))) + args[3:]
+    m_g = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    m_e = make_model(load_weights('seed0'), ['energy', 'gradient_force'])
+    o_g = torch.optim.Adam(m_g.parameters(), lr=1e-3, fused=True)
+    o_e = torch.optim.Adam(m_e.parameters(), lr=1e-3, fused=True)
+    step = GraphedTrainingStep(m_g, o_g, *args)
+    assert step._device_skip()
+    for k, a in enumerate((args, dense, args, dense)):
+        before = [p.detach().clone() for p in m_g.parameters()]
+        step(*a)
+        training_step(m_e, o_e, *a)
+        if k == 1:          # the dense batch did not fit: skipped on the device, nothing moved yet, one step pending
+            torch.cuda.synchronize()
+            assert step._pending and step.recaptures == 0
+            assert all(torch.equal(x, y.detach()) for x, y in zip(before, m_g.parameters()))
+    step.settle()
+    assert step.recaptures == 1 and not step._pending
+    assert int(o_g.state[next(iter(m_g.parameters()))]['step']) == 4
+    for (k, pe), (_, pg) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert float((pe.detach() - pg.detach()).abs().max()) < 2e-4 * max(float(pe.detach().abs().max()), 1e-3), k
 
 
 def test_reference_module_pickle_evaluates_like_the_reference():
