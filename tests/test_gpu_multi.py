@@ -181,6 +181,45 @@ def _train_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _graphed_dp_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from newtonnet_b200.train import GraphedTrainingStep
+        from oracle import newtonnet_oracle as O
+        z, pos, cell, batch = O.water_box(4)
+        rng = np.random.default_rng(rank)
+        pos = (pos + rng.normal(0, 0.02, pos.shape)).astype(np.float32)
+        t = lambda a, dt=None: torch.tensor(a, device=dev, dtype=dt)
+        args = (t(z), t(pos), t(cell), t(batch), t(rng.standard_normal(1), torch.float32), t(rng.standard_normal(pos.shape), torch.float32))
+        dense = (args[0], t((pos * 0.7).astype(np.float32)), t((cell * 0.7).astype(np.float32))) + args[3:]
+        model = _model(dev, ['energy', 'gradient_force'])
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+        step = GraphedTrainingStep(model, opt, *args)
+        assert step._device_skip()
+        # the second batch outgrows the edge capacity on rank 1 only: every rank must skip it on the device, then redo it
+        for a in (args, dense if rank == 1 else args, args):
+            step(*a)
+        step.settle()
+        assert step.recaptures == (1 if rank == 1 else 0), (rank, step.recaptures)
+        assert int(opt.state[next(iter(model.parameters()))]['step']) == 3
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert torch.equal(both[0], both[1])                    # data parallel: identical parameters on every rank
+        assert bool(torch.isfinite(flat).all())
+        dist.barrier(device_ids=[rank])
+    finally:
+        dist.destroy_process_group()
+
+
+@needs2
+def test_graphed_data_parallel_step_with_overflow_on_one_rank(tmp_path):
+    mp.spawn(_graphed_dp_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+
+
 @needs2
 def test_data_parallel_gradient_allreduce(tmp_path):
     mp.spawn(_train_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
