@@ -442,6 +442,100 @@ class SumMulC(torch.autograd.Function):
         return (MulB.apply(g, y3) if ctx.needs_input_grad[0] else None, MulB.apply(g, x3) if ctx.needs_input_grad[1] else None)
 
 
+# Products with a gathered operand (csrc/train_ops.cu k_ew_gmul / k_ew_grows): the node rows are read through the segment's
+# index inside the product, so neither forward nor the two backward sweeps materialise [E,F] / [E,3,F] copies of them.
+def _gmul_raw(a, b, r1, seg1, r2, seg2):
+    a = _c(a)
+    out = torch.empty_like(a)
+    n = a.shape[0]
+    if n:
+        b = None if b is None else _c(b)
+        r1 = _c(r1)
+        r2 = None if r2 is None else _c(r2)
+        L.check(L.load().nn_ew_gmul(a.data_ptr(), L.ptr(b), r1.data_ptr(), seg1.idx.data_ptr(), L.ptr(r2),
+                                    None if r2 is None else seg2.idx.data_ptr(), out.data_ptr(), n, _stream()), 'nn_ew_gmul')
+    return out
+
+
+class GMul(torch.autograd.Function):
+    """out[e,:] = a[e,:] * (b[e,:]) * r1[seg1.idx[e],:] * (r2[seg2.idx[e],:]);  b and r2 are optional, not both present.
+    m_e = me_e * mn_i * mn_j (reference models/newtonnet.py:211) is GMul(me, None, mn, seg_dst, mn, seg_src)."""
+
+    @staticmethod
+    def forward(ctx, a, b, r1, seg1, r2, seg2):
+        if b is not None and r2 is not None:
+            raise NotImplementedError('GMul: at most three factors')
+        ctx.save_for_backward(a, r1, *([b] if b is not None else []), *([r2] if r2 is not None else []))
+        ctx.has_b, ctx.has_r2, ctx.seg1, ctx.seg2 = b is not None, r2 is not None, seg1, seg2
+        return _gmul_raw(a, b, r1, seg1, r2, seg2)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        a, r1 = saved[0], saved[1]
+        b = saved[2] if ctx.has_b else None
+        r2 = saved[-1] if ctx.has_r2 else None
+        seg1, seg2 = ctx.seg1, ctx.seg2
+        ni = ctx.needs_input_grad
+        da = GMul.apply(g, b, r1, seg1, r2, seg2) if ni[0] else None
+        db = GMul.apply(g, a, r1, seg1, None, None) if (b is not None and ni[1]) else None
+        dr1 = dr2 = None
+        if ni[2]:               # everything but r1[i1], summed over the edges of each row
+            if r2 is not None:
+                rest = GMul.apply(g, a, r2, seg2, None, None)
+            else:
+                rest = Mul3.apply(g, a, b) if b is not None else g * a
+            dr1 = SegmentSum.apply(rest, seg1)
+        if r2 is not None and ni[4]:
+            dr2 = SegmentSum.apply(GMul.apply(g, a, r1, seg1, None, None), seg2)
+        return da, db, dr1, None, dr2, None
+
+
+def _grows_raw(mode, p, rows3, seg, out_shape):
+    out = torch.empty(out_shape, dtype=torch.float32, device=p.device)
+    if out_shape[0]:
+        L.check(L.load().nn_ew_grows(mode, _c(p).data_ptr(), _c(rows3).data_ptr(), seg.idx.data_ptr(), out.data_ptr(), out_shape[0],
+                                     _stream()), 'nn_ew_grows')
+    return out
+
+
+class MulBG(torch.autograd.Function):
+    """out[e,c,:] = x[e,:] * rows3[seg.idx[e],c,:]  -  e2_e * f_j (reference models/newtonnet.py:222-224) without the [E,3,F]
+    copy of the gathered force features."""
+
+    @staticmethod
+    def forward(ctx, x, rows3, seg):
+        ctx.save_for_backward(x, rows3)
+        ctx.seg = seg
+        return _grows_raw(0, x, rows3, seg, (x.shape[0], 3, x.shape[1]))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, rows3 = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        dx = SumMulCG.apply(g, rows3, ctx.seg) if ni[0] else None
+        dr = SegmentSum.apply(MulB.apply(x, g).reshape(x.shape[0], -1), ctx.seg).view_as(rows3) if ni[1] else None
+        return dx, dr, None
+
+
+class SumMulCG(torch.autograd.Function):
+    """out[e,:] = sum_c g3[e,c,:] * rows3[seg.idx[e],c,:]."""
+
+    @staticmethod
+    def forward(ctx, g3, rows3, seg):
+        ctx.save_for_backward(g3, rows3)
+        ctx.seg = seg
+        return _grows_raw(1, g3, rows3, seg, (g3.shape[0], g3.shape[2]))
+
+    @staticmethod
+    def backward(ctx, go):
+        g3, rows3 = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        dg = MulBG.apply(go, rows3, ctx.seg) if ni[0] else None
+        dr = SegmentSum.apply(MulB.apply(go, g3).reshape(g3.shape[0], -1), ctx.seg).view_as(rows3) if ni[1] else None
+        return dg, dr, None
+
+
 def _rbf_raw(op, k, a, x, freq):
     if k > 2:
         raise NotImplementedError('third-order differentiation through the radial basis is not implemented by the fused training kernels')
@@ -656,12 +750,11 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
         # K = 20 contraction through the same fp32-faithful GEMM (zero-padded to K = 128): a library matmul may
         # silently run in single-pass TF32 (TORCH_ALLOW_TF32_CUBLAS_OVERRIDE), which breaks gradient parity
         me = Gemm.apply(rbf_pad, Fn.pad(layer.message_edgepart.weight.t(), (0, 0, 0, F - rbf.shape[1])))
-        m = Mul3.apply(me, Gather.apply(mn, seg_dst), Gather.apply(mn, seg_src))
+        m = GMul.apply(me, None, mn, seg_dst, mn, seg_src)
         a = a + SegmentSum.apply(m, seg_dst)
         e1 = linear(silu(linear(m, layer.equiv_message1[0].weight)), layer.equiv_message1[2].weight)
         e2 = linear(silu(linear(m, layer.equiv_message2[0].weight)), layer.equiv_message2[2].weight)
-        fj = Gather.apply(f, seg_src).view(-1, 3, F)
-        vec = Outer.apply(e1, u) + MulB.apply(e2, fj)
+        vec = Outer.apply(e1, u) + MulBG.apply(e2, f.view(N, 3, F), seg_src)
         f = f + SegmentSum.apply(vec.reshape(-1, 3 * F), seg_dst)
         g = linear(f.view(3 * N, F), layer.equiv_update.weight).view(N, 3, F)
         a = a + SumMulC.apply(f.view(N, 3, F), g)

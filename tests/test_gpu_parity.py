@@ -418,6 +418,37 @@ def test_training_primitives_double_backward():
         assert float((a - b).abs().max() / b.abs().max()) < 1e-5
 
 
+def test_gathered_products_double_backward():
+    """GMul / MulBG / SumMulCG (products that read node rows through the edge index) composed twice by autograd against
+    torch-native fp64 indexing."""
+    from newtonnet_b200.train import GMul, MulBG, Segments, SegmentSum
+
+    def run(mine, dt):
+        g = torch.Generator().manual_seed(3)
+        N, E = 200, 3000
+        i1 = torch.randint(0, N, (E,), generator=g).sort().values.to(dev())
+        i2 = i1[torch.randperm(E, generator=g).to(dev())]
+        r = lambda *sh: torch.randn(*sh, generator=g).to(dev(), dt)
+        me, mn, f3, e2, tgt = r(E, 128).requires_grad_(True), r(N, 128).requires_grad_(True), r(N, 3, 128).requires_grad_(True), \
+            r(E, 128).requires_grad_(True), r(N, 128)
+        if mine:
+            s1, s2 = Segments(i1, N), Segments(i2, N)
+            m = GMul.apply(me, None, mn, s1, mn, s2)
+            v = MulBG.apply(e2 * m, f3, s2)
+            out = SegmentSum.apply(m, s1) + SegmentSum.apply(v.reshape(E, -1), s1).view(N, 3, 128).sum(1)
+        else:
+            m = me * mn[i1] * mn[i2]
+            v = (e2 * m).unsqueeze(1) * f3[i2]
+            out = torch.zeros(N, 128, dtype=dt, device=dev()).index_add(0, i1, m) + \
+                torch.zeros(N, 3, 128, dtype=dt, device=dev()).index_add(0, i1, v).sum(1)
+        first = torch.autograd.grad((out ** 2).sum(), [mn, f3], create_graph=True)
+        loss = ((first[0] - tgt) ** 2).mean() + (first[1] ** 2).mean()
+        return [t.double().cpu() for t in torch.autograd.grad(loss, [me, mn, f3, e2])]
+
+    for a, b in zip(run(True, torch.float32), run(False, torch.float64)):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-5
+
+
 def test_training_step_runs_and_reduces_loss():
     from newtonnet_b200.train import training_step
     d = dict(np.load(f'{GOLDEN}/train_mols24.npz'))
