@@ -412,6 +412,18 @@ NN_API int nn_ew_rows(int32_t mode, const float* p, const float* q3, const float
 NN_API int nn_ew_gmul(const float* a, const float* b, const float* r1, const int32_t* i1, const float* r2, const int32_t* i2,
                       float* out, int32_t n_rows, void* stream);
 NN_API int nn_ew_grows(int32_t mode, const float* p, const float* rows3, const int32_t* idx, float* out, int32_t n_rows, void* stream);
+/* Equivariant aggregation (models/newtonnet.py:219-226) without [E,3,F] intermediates; segments are CSR rows (row_ptr, optional
+ * perm = edge ids in row order), rows3 an [N,3,F] node table read through an edge index:
+ *   nn_seg_prod(u):       out[k,c,:] = sum_{e in seg(k)} x[e,:] * u[e,c]
+ *   nn_seg_prod(rows3):   out[k,c,:] = sum_{e in seg(k)} x[e,:] * rows3[idx[e],c,:]
+ *   nn_ew_g3(0, p = u):   out[e,:] = sum_c u[e,c] * rows3[idx[e],c,:]
+ *   nn_ew_g3(1, p = x):   out[e,c] = < rows3[idx[e],c,:], x[e,:] >
+ *   nn_ew_g3(2):          out[e,:] = sum_c rows3[idx[e],c,:] * rowsb[idxb[e],c,:]
+ * Closed under differentiation (each gradient is another member), fixed summation order. */
+NN_API int nn_seg_prod(const float* x, const float* u, const float* rows3, const int32_t* idx, const int32_t* perm,
+                       const int32_t* row_ptr, int32_t n_rows, float* out, void* stream);
+NN_API int nn_ew_g3(int32_t mode, const float* rows3, const int32_t* idx, const float* p, const float* rowsb, const int32_t* idxb,
+                    float* out, int32_t n_rows, void* stream);
 /* SiLU with its first two derivatives (layers/activations.py:13 nn.SiLU under autograd twice): mode 0 out = silu(x);
  * mode 1 out = a * silu'(x); mode 2 out = a * b * silu''(x). */
 /* Radial basis R_n(x) = env(x) sin(f_n x) / x (representations.py:166-169,233) with its x-derivatives of order k = 0..2:

@@ -233,7 +233,99 @@ k_ew_grows(const float* __restrict__ p, const float* __restrict__ rows3, const i
     }
 }
 
+// Equivariant aggregation without [E,3,F] tensors (reference models/newtonnet.py:219-226: delta f_i = sum_{e->i} e1_e u_e +
+// e2_e * f_j).  Five kernels that are closed under differentiation; rows3 is an [N,3,F] node table read
+// through an edge index, segments are rows of a CSR (perm = edge order within the rows, or null):
+//   k_seg_outer:   out[k,c,:] = sum_{e in seg(k)} x[e,:] * u[e,c]
+//   k_seg_mulbg:   out[k,c,:] = sum_{e in seg(k)} x[e,:] * rows3[idx[e],c,:]
+//   k_ew_g3<0>:    out[e,:]   = sum_c u[e,c] * rows3[idx[e],c,:]                      (contract_c, gathered)
+//   k_ew_g3<1>:    out[e,c]   = < rows3[idx[e],c,:], x[e,:] >                         (row_dot, gathered)
+//   k_ew_g3<2>:    out[e,:]   = sum_c rows3[idx[e],c,:] * rowsb[idxb[e],c,:]          (sum_mul_c, both gathered)
+template <bool GATHER>
+__global__ void __launch_bounds__(256)
+k_seg_prod(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ rows3, const int* __restrict__ idx,
+           const int* __restrict__ perm, const int* __restrict__ row_ptr, int n_rows, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= n_rows) return;
+    float4 acc[3] = {f4_zero(), f4_zero(), f4_zero()};
+    const int r0 = row_ptr[k], r1 = row_ptr[k + 1];
+    for (int t = r0; t < r1; ++t) {
+        const int e = perm ? perm[t] : t;
+        const float4 xv = ld4(x + (size_t)e * kF + 4 * lane);
+        if (GATHER) {
+            const size_t g = (size_t)idx[e] * 3 * kF + 4 * lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] = f4_fma(xv, ld4(rows3 + g + c * kF), acc[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] = f4_fma(u[3 * e + c], xv, acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st4(out + ((size_t)k * 3 + c) * kF + 4 * lane, acc[c]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_ew_g3(const float* __restrict__ rows3, const int* __restrict__ idx, const float* __restrict__ p, const float* __restrict__ rowsb,
+        const int* __restrict__ idxb, float* __restrict__ out, int n) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= n) return;
+    const size_t g = (size_t)idx[e] * 3 * kF + 4 * lane, r = (size_t)e * kF + 4 * lane;
+    if (MODE == 0) {            // p = u [n,3]
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc = f4_fma(p[3 * e + c], ld4(rows3 + g + c * kF), acc);
+        st4(out + r, acc);
+    } else if (MODE == 1) {     // p = x [n,F]
+        const float4 x = ld4(p + r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float s = warp_sum(f4_dot(ld4(rows3 + g + c * kF), x));
+            if (lane == 0) out[3 * e + c] = s;
+        }
+    } else {
+        const size_t gb = (size_t)idxb[e] * 3 * kF + 4 * lane;
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc = f4_fma(ld4(rows3 + g + c * kF), ld4(rowsb + gb + c * kF), acc);
+        st4(out + r, acc);
+    }
+}
+
 }  // namespace
+
+extern "C" int nn_seg_prod(const float* x, const float* u, const float* rows3, const int32_t* idx, const int32_t* perm,
+                           const int32_t* row_ptr, int32_t n_rows, float* out, void* stream) {
+    NN_REQUIRE(x && row_ptr && out, "null pointer");
+    NN_REQUIRE((u != nullptr) != (rows3 != nullptr), "exactly one of u (outer) and rows3 (gathered product)");
+    NN_REQUIRE(!rows3 || idx, "rows3 needs idx");
+    if (n_rows <= 0) return 0;
+    const int grid = nn_ceil_div(n_rows, 8);
+    if (rows3) k_seg_prod<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, u, rows3, idx, perm, row_ptr, n_rows, out);
+    else k_seg_prod<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, u, rows3, idx, perm, row_ptr, n_rows, out);
+    NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_seg_prod");
+    return 0;
+}
+
+extern "C" int nn_ew_g3(int32_t mode, const float* rows3, const int32_t* idx, const float* p, const float* rowsb, const int32_t* idxb,
+                        float* out, int32_t n_rows, void* stream) {
+    NN_REQUIRE(rows3 && idx && out, "null pointer");
+    NN_REQUIRE(mode >= 0 && mode <= 2, "mode 0..2");
+    NN_REQUIRE(mode == 2 ? (rowsb && idxb) : (p != nullptr), "missing operand");
+    if (n_rows <= 0) return 0;
+    const int grid = nn_ceil_div(n_rows, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == 0) k_ew_g3<0><<<grid, 256, 0, s>>>(rows3, idx, p, rowsb, idxb, out, n_rows);
+    else if (mode == 1) k_ew_g3<1><<<grid, 256, 0, s>>>(rows3, idx, p, rowsb, idxb, out, n_rows);
+    else k_ew_g3<2><<<grid, 256, 0, s>>>(rows3, idx, p, rowsb, idxb, out, n_rows);
+    NN_LAUNCHED(1);
+    NN_CHECK_LAUNCH("nn_ew_g3");
+    return 0;
+}
 
 extern "C" int nn_ew_gmul(const float* a, const float* b, const float* r1, const int32_t* i1, const float* r2, const int32_t* i2,
                           float* out, int32_t n_rows, void* stream) {

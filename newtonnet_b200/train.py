@@ -536,6 +536,115 @@ class SumMulCG(torch.autograd.Function):
         return dg, dr, None
 
 
+# Equivariant aggregation without [E,3,F] tensors (csrc/train_ops.cu k_seg_prod / k_ew_g3).  Five Functions, each gradient
+# another member:   SegOuter(x,u;s)      d_x = ContractCG(go,u;s)          d_u = RowDotG(go,x;s)
+#                   SegMulBG(x,r;so,si)  d_x = SumMulCGG(go,so,r,si)       d_r = SegMulBG(x,go;si,so)
+#                   ContractCG(r,u;s)    d_r = SegOuter(go,u;s)            d_u = RowDotG(r,go;s)
+#                   RowDotG(r,x;s)       d_r = SegOuter(x,go;s)            d_x = ContractCG(r,go;s)
+#                   SumMulCGG(a,sa,b,sb) d_a = SegMulBG(go,b;sa,sb)        d_b = SegMulBG(go,a;sb,sa)
+def _seg_prod_raw(x, u, rows3, seg_in, seg_out):
+    x = _c(x)
+    out = torch.zeros(seg_out.n_rows, 3, x.shape[1], dtype=torch.float32, device=x.device)
+    if x.shape[0]:
+        L.check(L.load().nn_seg_prod(x.data_ptr(), None if u is None else _c(u).data_ptr(), None if rows3 is None else _c(rows3).data_ptr(),
+                                     None if seg_in is None else seg_in.idx.data_ptr(), L.ptr(seg_out.perm), seg_out.row_ptr.data_ptr(),
+                                     seg_out.n_rows, out.data_ptr(), _stream()), 'nn_seg_prod')
+    return out
+
+
+def _g3_raw(mode, rows3, seg, p, rowsb, segb, out_shape):
+    out = torch.empty(out_shape, dtype=torch.float32, device=rows3.device)
+    if out_shape[0]:
+        L.check(L.load().nn_ew_g3(mode, _c(rows3).data_ptr(), seg.idx.data_ptr(), None if p is None else _c(p).data_ptr(),
+                                  None if rowsb is None else _c(rowsb).data_ptr(), None if segb is None else segb.idx.data_ptr(),
+                                  out.data_ptr(), out_shape[0], _stream()), 'nn_ew_g3')
+    return out
+
+
+class SegOuter(torch.autograd.Function):
+    """out[k,c,:] = sum_{e in seg(k)} x[e,:] * u[e,c];  x [E,F], u [E,3] -> [N,3,F]."""
+
+    @staticmethod
+    def forward(ctx, x, u, seg):
+        ctx.save_for_backward(x, u)
+        ctx.seg = seg
+        return _seg_prod_raw(x, u, None, None, seg)
+
+    @staticmethod
+    def backward(ctx, go):
+        x, u = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        return (ContractCG.apply(go, u, ctx.seg) if ni[0] else None, RowDotG.apply(go, x, ctx.seg) if ni[1] else None, None)
+
+
+class SegMulBG(torch.autograd.Function):
+    """out[k,c,:] = sum_{e in seg_out(k)} x[e,:] * rows3[seg_in.idx[e],c,:];  x [E,F], rows3 [N,3,F] -> [N,3,F]."""
+
+    @staticmethod
+    def forward(ctx, x, rows3, seg_out, seg_in):
+        ctx.save_for_backward(x, rows3)
+        ctx.seg_out, ctx.seg_in = seg_out, seg_in
+        return _seg_prod_raw(x, None, rows3, seg_in, seg_out)
+
+    @staticmethod
+    def backward(ctx, go):
+        x, rows3 = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        dx = SumMulCGG.apply(go, ctx.seg_out, rows3, ctx.seg_in) if ni[0] else None
+        dr = SegMulBG.apply(x, go, ctx.seg_in, ctx.seg_out) if ni[1] else None
+        return dx, dr, None, None
+
+
+class ContractCG(torch.autograd.Function):
+    """out[e,:] = sum_c u[e,c] * rows3[seg.idx[e],c,:]."""
+
+    @staticmethod
+    def forward(ctx, rows3, u, seg):
+        ctx.save_for_backward(rows3, u)
+        ctx.seg = seg
+        return _g3_raw(0, rows3, seg, u, None, None, (u.shape[0], rows3.shape[2]))
+
+    @staticmethod
+    def backward(ctx, go):
+        rows3, u = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        return (SegOuter.apply(go, u, ctx.seg) if ni[0] else None, RowDotG.apply(rows3, go, ctx.seg) if ni[1] else None, None)
+
+
+class RowDotG(torch.autograd.Function):
+    """out[e,c] = < rows3[seg.idx[e],c,:], x[e,:] >."""
+
+    @staticmethod
+    def forward(ctx, rows3, x, seg):
+        ctx.save_for_backward(rows3, x)
+        ctx.seg = seg
+        return _g3_raw(1, rows3, seg, x, None, None, (x.shape[0], 3))
+
+    @staticmethod
+    def backward(ctx, go):
+        rows3, x = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        return (SegOuter.apply(x, go, ctx.seg) if ni[0] else None, ContractCG.apply(rows3, go, ctx.seg) if ni[1] else None, None)
+
+
+class SumMulCGG(torch.autograd.Function):
+    """out[e,:] = sum_c a3[seg_a.idx[e],c,:] * b3[seg_b.idx[e],c,:]."""
+
+    @staticmethod
+    def forward(ctx, a3, seg_a, b3, seg_b):
+        ctx.save_for_backward(a3, b3)
+        ctx.seg_a, ctx.seg_b = seg_a, seg_b
+        return _g3_raw(2, a3, seg_a, None, b3, seg_b, (seg_a.idx.shape[0], a3.shape[2]))
+
+    @staticmethod
+    def backward(ctx, go):
+        a3, b3 = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        da = SegMulBG.apply(go, b3, ctx.seg_a, ctx.seg_b) if ni[0] else None
+        db = SegMulBG.apply(go, a3, ctx.seg_b, ctx.seg_a) if ni[2] else None
+        return da, None, db, None
+
+
 def _rbf_raw(op, k, a, x, freq):
     if k > 2:
         raise NotImplementedError('third-order differentiation through the radial basis is not implemented by the fused training kernels')
@@ -754,8 +863,8 @@ def differentiable_forward(model, z, pos, cell, batch, static_nl=None):
         a = a + SegmentSum.apply(m, seg_dst)
         e1 = linear(silu(linear(m, layer.equiv_message1[0].weight)), layer.equiv_message1[2].weight)
         e2 = linear(silu(linear(m, layer.equiv_message2[0].weight)), layer.equiv_message2[2].weight)
-        vec = Outer.apply(e1, u) + MulBG.apply(e2, f.view(N, 3, F), seg_src)
-        f = f + SegmentSum.apply(vec.reshape(-1, 3 * F), seg_dst)
+        # delta f_i = sum_{e->i} (e1_e u_e + e2_e * f_j): two segment products, no [E,3,F] tensor anywhere in the step
+        f = f + (SegOuter.apply(e1, u, seg_dst) + SegMulBG.apply(e2, f.view(N, 3, F), seg_dst, seg_src)).reshape(N, 3 * F)
         g = linear(f.view(3 * N, F), layer.equiv_update.weight).view(N, 3, F)
         a = a + SumMulC.apply(f.view(N, 3, F), g)
         if layer.layer_norm is not None:

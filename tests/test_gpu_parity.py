@@ -449,6 +449,36 @@ def test_gathered_products_double_backward():
         assert float((a - b).abs().max() / b.abs().max()) < 2e-5
 
 
+def test_segment_products_double_backward():
+    """SegOuter / SegMulBG and their gradient family (ContractCG, RowDotG, SumMulCGG): delta f_i = sum_{e->i} e1_e u_e + e2_e f_j
+    (reference models/newtonnet.py:219-226) composed twice by autograd against torch-native fp64 indexing; the second index is
+    grouped through a permutation, as the source-atom segments of the neighbour list are."""
+    from newtonnet_b200.train import SegMulBG, SegOuter, Segments
+
+    def run(mine, dt):
+        g = torch.Generator().manual_seed(5)
+        N, E = 150, 2500
+        i1 = torch.randint(0, N, (E,), generator=g).sort().values.to(dev())
+        i2 = i1[torch.randperm(E, generator=g).to(dev())]
+        r = lambda *sh: torch.randn(*sh, generator=g).to(dev(), dt)
+        e1, e2, u, f3, tgt = r(E, 128).requires_grad_(True), r(E, 128).requires_grad_(True), r(E, 3).requires_grad_(True), \
+            r(N, 3, 128).requires_grad_(True), r(N, 3, 128)
+        if mine:
+            s1, s2 = Segments(i1, N), Segments(i2, N)
+            out = SegOuter.apply(e1, u, s1) + SegMulBG.apply(e2, f3, s1, s2)
+            out = out + SegMulBG.apply(e1, out, s1, s2)           # a second layer reading the first one's output
+        else:
+            z = lambda: torch.zeros(N, 3, 128, dtype=dt, device=dev())
+            out = z().index_add(0, i1, e1.unsqueeze(1) * u.unsqueeze(2)) + z().index_add(0, i1, e2.unsqueeze(1) * f3[i2])
+            out = out + z().index_add(0, i1, e1.unsqueeze(1) * out[i2])
+        first = torch.autograd.grad((out ** 2).sum(), [u, f3, e1], create_graph=True)
+        loss = ((first[1] - tgt) ** 2).mean() + (first[0] ** 2).mean() + (first[2] ** 2).mean()
+        return [t.double().cpu() for t in torch.autograd.grad(loss, [e1, e2, u, f3])]
+
+    for a, b in zip(run(True, torch.float32), run(False, torch.float64)):
+        assert float((a - b).abs().max() / b.abs().max()) < 5e-5
+
+
 def test_training_step_runs_and_reduces_loss():
     from newtonnet_b200.train import training_step
     d = dict(np.load(f'{GOLDEN}/train_mols24.npz'))
