@@ -404,14 +404,11 @@ NN_API int nn_gemm128_tn_acc(const float* X, const float* Y, int32_t m, float* o
  *     4 sum_mul_c  out[n,F]   = sum_c q3[e,c,:] * p3[e,c,:]   (the second [n,3,F] operand is passed as p) */
 NN_API int nn_ew_mul3(const float* a, const float* b, const float* c, float* out, int64_t n_floats, void* stream);
 NN_API int nn_ew_rows(int32_t mode, const float* p, const float* q3, const float* u, float* out, int32_t n_rows, void* stream);
-/* The same products with a GATHERED operand (no [E,F] / [E,3,F] copy of the node rows is materialised):
+/* The message product with GATHERED operands (no [E,F] copy of the node rows is materialised):
  *   nn_ew_gmul:        out[e,:] = a[e,:] * (b ? b[e,:] : 1) * r1[i1[e],:] * (r2 ? r2[i2[e],:] : 1)   (models/newtonnet.py:211)
- *   nn_ew_grows(0):    out[e,c,:] = p[e,:] * rows3[idx[e],c,:]                                        (models/newtonnet.py:222-224)
- *   nn_ew_grows(1):    out[e,:] = sum_c p[e,c,:] * rows3[idx[e],c,:]
- * Closed under differentiation together with nn_ew_mul3 / nn_ew_rows / nn_segment_sum. */
+ * Closed under differentiation together with nn_ew_mul3 / nn_segment_sum. */
 NN_API int nn_ew_gmul(const float* a, const float* b, const float* r1, const int32_t* i1, const float* r2, const int32_t* i2,
                       float* out, int32_t n_rows, void* stream);
-NN_API int nn_ew_grows(int32_t mode, const float* p, const float* rows3, const int32_t* idx, float* out, int32_t n_rows, void* stream);
 /* Equivariant aggregation (models/newtonnet.py:219-226) without [E,3,F] intermediates; segments are CSR rows (row_ptr, optional
  * perm = edge ids in row order), rows3 an [N,3,F] node table read through an edge index:
  *   nn_seg_prod(u):       out[k,c,:] = sum_{e in seg(k)} x[e,:] * u[e,c]

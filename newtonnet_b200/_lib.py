@@ -120,7 +120,6 @@ SYMBOLS = {
     'nn_ew_mul3': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'nn_ew_rows': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_ew_gmul': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
-    'nn_ew_grows': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_seg_prod': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),
     'nn_ew_g3': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     'nn_ew_silu': (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_int64, _fp]),

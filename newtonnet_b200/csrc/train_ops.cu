@@ -196,11 +196,9 @@ k_ew_rows(const float* __restrict__ p, const float* __restrict__ q3, const float
     }
 }
 
-// Row products with a GATHERED operand: the gathers rows[idx[e]] that feed the products of models/newtonnet.py:211,219-226
-// read straight from the (L2-resident, N x 512 B) node table instead of materialising an [E,F] / [E,3,F] copy first.
+// Row product with GATHERED operands: the gathers mn[idx[e]] that feed the message of models/newtonnet.py:211 read straight
+// from the (L2-resident, N x 512 B) node table instead of materialising [E,F] copies first.
 //   k_ew_gmul:      out[e,:] = a[e,:] * (b ? b[e,:] : 1) * r1[i1[e],:] * (r2 ? r2[i2[e],:] : 1)
-//   k_ew_grows<0>:  out[e,c,:] = x[e,:] * rows3[idx[e],c,:]               (mul_b with a gathered [N,3,F] operand)
-//   k_ew_grows<1>:  out[e,:]   = sum_c g3[e,c,:] * rows3[idx[e],c,:]      (sum_mul_c with a gathered operand)
 __global__ void __launch_bounds__(256)
 k_ew_gmul(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ r1, const int* __restrict__ i1,
           const float* __restrict__ r2, const int* __restrict__ i2, float* __restrict__ out, int n) {
@@ -212,25 +210,6 @@ k_ew_gmul(const float* __restrict__ a, const float* __restrict__ b, const float*
     if (b) v = f4_mul(v, ld4(b + r));
     if (r2) v = f4_mul(v, ld4(r2 + (size_t)i2[e] * kF + 4 * lane));
     st4(out + r, v);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_ew_grows(const float* __restrict__ p, const float* __restrict__ rows3, const int* __restrict__ idx, float* __restrict__ out, int n) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (e >= n) return;
-    const size_t r = (size_t)e * kF + 4 * lane, r3 = (size_t)e * 3 * kF + 4 * lane, g3 = (size_t)idx[e] * 3 * kF + 4 * lane;
-    if (MODE == 0) {
-        const float4 x = ld4(p + r);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) st4(out + r3 + c * kF, f4_mul(x, ld4(rows3 + g3 + c * kF)));
-    } else {
-        float4 acc = f4_zero();
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc = f4_fma(ld4(p + r3 + c * kF), ld4(rows3 + g3 + c * kF), acc);
-        st4(out + r, acc);
-    }
 }
 
 // Equivariant aggregation without [E,3,F] tensors (reference models/newtonnet.py:219-226: delta f_i = sum_{e->i} e1_e u_e +
@@ -334,18 +313,6 @@ extern "C" int nn_ew_gmul(const float* a, const float* b, const float* r1, const
     if (n_rows <= 0) return 0;
     k_ew_gmul<<<nn_ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(a, b, r1, i1, r2, i2, out, n_rows); NN_LAUNCHED(1);
     NN_CHECK_LAUNCH("nn_ew_gmul");
-    return 0;
-}
-
-extern "C" int nn_ew_grows(int32_t mode, const float* p, const float* rows3, const int32_t* idx, float* out, int32_t n_rows, void* stream) {
-    NN_REQUIRE(p && rows3 && idx && out, "null pointer");
-    NN_REQUIRE(mode == 0 || mode == 1, "mode 0..1");
-    if (n_rows <= 0) return 0;
-    const int grid = nn_ceil_div(n_rows, 8);
-    if (mode == 0) k_ew_grows<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p, rows3, idx, out, n_rows);
-    else k_ew_grows<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p, rows3, idx, out, n_rows);
-    NN_LAUNCHED(1);
-    NN_CHECK_LAUNCH("nn_ew_grows");
     return 0;
 }
 

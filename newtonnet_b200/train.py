@@ -329,7 +329,8 @@ class SegmentSum(torch.autograd.Function):
         src = _c(src)
         ctx.seg = seg
         width = src.shape[1]
-        out = torch.zeros(seg.n_rows, width, dtype=torch.float32, device=src.device)
+        # the kernel writes every output row (empty segments get zeros): no fill kernel in front of it
+        out = (torch.empty if src.shape[0] else torch.zeros)(seg.n_rows, width, dtype=torch.float32, device=src.device)
         if src.shape[0]:
             L.check(L.load().nn_segment_sum(src.data_ptr(), L.ptr(seg.perm), seg.row_ptr.data_ptr(), seg.n_rows, width,
                                             out.data_ptr(), _stream()), 'nn_segment_sum')
@@ -442,8 +443,8 @@ class SumMulC(torch.autograd.Function):
         return (MulB.apply(g, y3) if ctx.needs_input_grad[0] else None, MulB.apply(g, x3) if ctx.needs_input_grad[1] else None)
 
 
-# Products with a gathered operand (csrc/train_ops.cu k_ew_gmul / k_ew_grows): the node rows are read through the segment's
-# index inside the product, so neither forward nor the two backward sweeps materialise [E,F] / [E,3,F] copies of them.
+# Product with gathered operands (csrc/train_ops.cu k_ew_gmul): the node rows are read through the segments' indices inside
+# the product, so neither forward nor the two backward sweeps materialise [E,F] copies of them.
 def _gmul_raw(a, b, r1, seg1, r2, seg2):
     a = _c(a)
     out = torch.empty_like(a)
@@ -491,51 +492,6 @@ class GMul(torch.autograd.Function):
         return da, db, dr1, None, dr2, None
 
 
-def _grows_raw(mode, p, rows3, seg, out_shape):
-    out = torch.empty(out_shape, dtype=torch.float32, device=p.device)
-    if out_shape[0]:
-        L.check(L.load().nn_ew_grows(mode, _c(p).data_ptr(), _c(rows3).data_ptr(), seg.idx.data_ptr(), out.data_ptr(), out_shape[0],
-                                     _stream()), 'nn_ew_grows')
-    return out
-
-
-class MulBG(torch.autograd.Function):
-    """out[e,c,:] = x[e,:] * rows3[seg.idx[e],c,:]  -  e2_e * f_j (reference models/newtonnet.py:222-224) without the [E,3,F]
-    copy of the gathered force features."""
-
-    @staticmethod
-    def forward(ctx, x, rows3, seg):
-        ctx.save_for_backward(x, rows3)
-        ctx.seg = seg
-        return _grows_raw(0, x, rows3, seg, (x.shape[0], 3, x.shape[1]))
-
-    @staticmethod
-    def backward(ctx, g):
-        x, rows3 = ctx.saved_tensors
-        ni = ctx.needs_input_grad
-        dx = SumMulCG.apply(g, rows3, ctx.seg) if ni[0] else None
-        dr = SegmentSum.apply(MulB.apply(x, g).reshape(x.shape[0], -1), ctx.seg).view_as(rows3) if ni[1] else None
-        return dx, dr, None
-
-
-class SumMulCG(torch.autograd.Function):
-    """out[e,:] = sum_c g3[e,c,:] * rows3[seg.idx[e],c,:]."""
-
-    @staticmethod
-    def forward(ctx, g3, rows3, seg):
-        ctx.save_for_backward(g3, rows3)
-        ctx.seg = seg
-        return _grows_raw(1, g3, rows3, seg, (g3.shape[0], g3.shape[2]))
-
-    @staticmethod
-    def backward(ctx, go):
-        g3, rows3 = ctx.saved_tensors
-        ni = ctx.needs_input_grad
-        dg = MulBG.apply(go, rows3, ctx.seg) if ni[0] else None
-        dr = SegmentSum.apply(MulB.apply(go, g3).reshape(g3.shape[0], -1), ctx.seg).view_as(rows3) if ni[1] else None
-        return dg, dr, None
-
-
 # Equivariant aggregation without [E,3,F] tensors (csrc/train_ops.cu k_seg_prod / k_ew_g3).  Five Functions, each gradient
 # another member:   SegOuter(x,u;s)      d_x = ContractCG(go,u;s)          d_u = RowDotG(go,x;s)
 #                   SegMulBG(x,r;so,si)  d_x = SumMulCGG(go,so,r,si)       d_r = SegMulBG(x,go;si,so)
@@ -544,7 +500,7 @@ class SumMulCG(torch.autograd.Function):
 #                   SumMulCGG(a,sa,b,sb) d_a = SegMulBG(go,b;sa,sb)        d_b = SegMulBG(go,a;sb,sa)
 def _seg_prod_raw(x, u, rows3, seg_in, seg_out):
     x = _c(x)
-    out = torch.zeros(seg_out.n_rows, 3, x.shape[1], dtype=torch.float32, device=x.device)
+    out = (torch.empty if x.shape[0] else torch.zeros)(seg_out.n_rows, 3, x.shape[1], dtype=torch.float32, device=x.device)
     if x.shape[0]:
         L.check(L.load().nn_seg_prod(x.data_ptr(), None if u is None else _c(u).data_ptr(), None if rows3 is None else _c(rows3).data_ptr(),
                                      None if seg_in is None else seg_in.idx.data_ptr(), L.ptr(seg_out.perm), seg_out.row_ptr.data_ptr(),

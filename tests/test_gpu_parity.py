@@ -419,9 +419,9 @@ def test_training_primitives_double_backward():
 
 
 def test_gathered_products_double_backward():
-    """GMul / MulBG / SumMulCG (products that read node rows through the edge index) composed twice by autograd against
-    torch-native fp64 indexing."""
-    from newtonnet_b200.train import GMul, MulBG, Segments, SegmentSum
+    """GMul (the message product reading node rows through the edge index) feeding a segment product, composed twice by
+    autograd against torch-native fp64 indexing."""
+    from newtonnet_b200.train import GMul, SegMulBG, Segments, SegmentSum
 
     def run(mine, dt):
         g = torch.Generator().manual_seed(3)
@@ -434,8 +434,7 @@ def test_gathered_products_double_backward():
         if mine:
             s1, s2 = Segments(i1, N), Segments(i2, N)
             m = GMul.apply(me, None, mn, s1, mn, s2)
-            v = MulBG.apply(e2 * m, f3, s2)
-            out = SegmentSum.apply(m, s1) + SegmentSum.apply(v.reshape(E, -1), s1).view(N, 3, 128).sum(1)
+            out = SegmentSum.apply(m, s1) + SegMulBG.apply(e2 * m, f3, s1, s2).sum(1)
         else:
             m = me * mn[i1] * mn[i2]
             v = (e2 * m).unsqueeze(1) * f3[i2]
