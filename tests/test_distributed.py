@@ -112,6 +112,14 @@ def _grad_worker(rank, world, port):
         assert torch.allclose(params[0].grad, torch.full((5, 3), 1.5))
         assert torch.allclose(params[1].grad, torch.arange(7.0) * 1.5)
         assert params[2].grad is None and torch.equal(params[3].grad, torch.zeros(4))
+        # condition flags ride along in the bucket and come back SUMMED (the edge-overflow flag of GraphedTrainingStep: every
+        # rank must see that one of them overflowed), the gradients are still averaged
+        params[0].grad = torch.full((5, 3), float(rank + 1))
+        flags = torch.tensor([1.0 if rank == 1 else 0.0, 2.0])
+        flat = allreduce_gradients(params, flags=flags)
+        assert flat.numel() == 15 + 7 + 4
+        assert torch.equal(flags, torch.tensor([1.0, 4.0]))
+        assert torch.allclose(params[0].grad, torch.full((5, 3), 1.5))
     finally:
         dist.destroy_process_group()
 
