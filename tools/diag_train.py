@@ -1,7 +1,7 @@
 """Diagnostics of the training path: loss / force / gradient errors vs the fp64 reference golden, per backend."""
 import sys
 import numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')   # run from the repo root: python tools/diag_train.py [mols24|water81]
 from newtonnet_b200 import _lib as L
 from newtonnet_b200.compat import model_from_state_dict
 from oracle import newtonnet_oracle as O
