@@ -134,3 +134,27 @@ def test_hessian_matches_reference():
     h = O.hessian(w, d['z'], d['pos'], np.zeros((1, 3, 3)), np.zeros(21, dtype=np.int64))
     assert h.shape == (21, 3, 21, 3)
     assert np.abs(h - d['hessian']).max() < 1e-4        # golden positions are stored in fp32
+
+
+def test_cluster_cut_reproduces_periodic_forces():
+    """oracle/cluster.py, the checker of the 98k-atom box (tests/test_gpu_c4.py, bench.py's in-run parity record): forces of
+    the atoms at the centre of a NON-periodic cluster of radius r_dest + 2 * n_layers * cutoff equal the forces of the full
+    periodic system.  Pinned here where the full periodic oracle still runs: a one-layer model (receptive field 10 A) on
+    a 1,536-atom water box (L = 24.8 A)."""
+    from oracle.cluster import oracle_cluster_forces
+    w = load_weights('seed0')
+    w1 = {k: v for k, v in w.items() if not k.startswith('interaction_layers.') or k.startswith('interaction_layers.0.')}
+    assert O.n_layers(w1) == 1
+    z, pos, cell, batch = O.water_box(8)
+    ei, disp = O.radius_graph_cell_list(pos, cell, batch)
+    full = O.forward_analytic(w1, z, pos, cell, batch, dtype=torch.float64, edge_index=ei, disp=disp)
+    for center in (0, 700, 1535):
+        idx, f, info = oracle_cluster_forces(z, pos, cell, w1, center, n_layers=1)
+        assert info['destination_atoms'] >= 1 and info['cluster_atoms'] < len(z)
+        ref = np.asarray(full['forces'])[idx]
+        assert np.abs(ref).max() > 1e-3
+        # the cluster's positions are re-centred and rounded to fp32 again: displacements differ by ~1e-6 A
+        assert np.abs(f - ref).max() < (2e-5 if info['oracle_dtype'] == 'float64' else 1e-4), (center, info)
+    # one layer too few in the radius and the forces at the centre are wrong: the check has teeth
+    idx, f, info = oracle_cluster_forces(z, pos, cell, w1, 700, n_layers=0)
+    assert np.abs(f - np.asarray(full['forces'])[idx]).max() > 1e-3
