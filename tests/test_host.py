@@ -182,3 +182,25 @@ def _as_plain_module(m):
     f = Foreign()
     f.__dict__.update(m.__dict__)
     return f
+
+
+def test_weight_gradient_routing_modes_nest_and_restore():
+    """newtonnet_b200.train: 'skip' while the forces are derived (no X^T dY formed), restored on exit, also when nested or
+    when the body raises; routing itself needs no GPU."""
+    import torch
+    from newtonnet_b200 import train
+    assert train._weight_grad_mode == 'autograd'
+    W = torch.nn.Parameter(torch.zeros(128, 128))
+    with train._skip_weight_grads():
+        assert train._weight_grad_mode == 'skip'
+        assert train._weight_grad(W, torch.zeros(4, 128), torch.zeros(4, 128)) is None      # nothing launched
+        with train._skip_weight_grads():
+            assert train._weight_grad_mode == 'skip'
+        assert train._weight_grad_mode == 'skip'
+    assert train._weight_grad_mode == 'autograd'
+    try:
+        with train._skip_weight_grads():
+            raise KeyError('x')
+    except KeyError:
+        pass
+    assert train._weight_grad_mode == 'autograd'
